@@ -1,0 +1,62 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (oracle/ref_runner.py). TEST INFRASTRUCTURE.
+
+Run in the build container only:  python oracle/gen_golden.py [tiny8 tiny16 c1]
+The fixtures are committed; the GPU box never needs /root/reference.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from motionclone_b200.synthetic import UNET_SD15_CONFIG, UNET_TINY_CONFIG, synthetic_inputs  # noqa: E402
+from oracle.ref_runner import run_reference  # noqa: E402
+
+BASE = dict(cfg_scale=7.5, negative_prompt="", warm_up_steps=10, cool_up_steps=10, motion_guidance_weight=2000,
+            motion_guidance_blocks=["up_blocks.1"], add_noise_step=400)
+
+CASES = {
+    # name: (unet config name, inference cfg, input seed)
+    "tiny8": ("tiny", dict(BASE, inference_steps=6, guidance_steps=3, guidance_scale=0.3, video_length=8, height=128,
+                           width=128), 42),
+    "tiny16": ("tiny", dict(BASE, inference_steps=5, guidance_steps=3, guidance_scale=0.4, video_length=16, height=128,
+                            width=128, warm_up_steps=2, cool_up_steps=2), 52),
+    # BASELINE.json configs[0]: t2v_camera, 8x256x256, 10 DDIM steps, SD1.5 widths (plumbing case, CPU-runnable)
+    "c1": ("sd15", dict(BASE, inference_steps=10, guidance_steps=5, guidance_scale=0.3, video_length=8, height=256,
+                        width=256), 42),
+}
+
+
+def main(names):
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for name in names:
+        ucfg_name, icfg, seed = CASES[name]
+        ucfg = UNET_TINY_CONFIG if ucfg_name == "tiny" else UNET_SD15_CONFIG
+        inp = synthetic_inputs(icfg["video_length"], icfg["height"], icfg["width"], ucfg["cross_attention_dim"], seed)
+        t0 = time.time()
+        out, pipe = run_reference(ucfg, icfg, inp, f"/tmp/_golden_{name}.pt", weight_seed=42)
+        arrays = {k: (v.numpy() if torch.is_tensor(v) else np.array(v)) for k, v in out.items()}
+        arrays["meta"] = np.array(json.dumps(dict(case=name, unet=ucfg_name, infer=icfg, input_seed=seed,
+                                                   weight_seed=42, torch=torch.__version__,
+                                                   generator="oracle/gen_golden.py", reference="/root/reference @7724ee8",
+                                                   seconds=round(time.time() - t0, 1))))
+        if name == "c1":  # keep the fixture small: drop the full prob tensor and intermediate latents
+            arrays.pop("extract_probs_0", None)
+            arrays["latents_per_step"] = arrays["latents_per_step"][[0, 4, 5, 9]]
+            arrays["latents_steps_kept"] = np.array([0, 4, 5, 9])
+        path = os.path.join(ROOT, "tests", "golden", f"ref_{name}.npz")
+        np.savez_compressed(path, **arrays)
+        print(name, "->", path, os.path.getsize(path) // 1024, "KiB", round(time.time() - t0, 1), "s", flush=True)
+        if name != "c1":
+            shapes = {k: list(v.shape) for k, v in pipe.unet.state_dict().items()}
+            with open(os.path.join(ROOT, "tests", "golden", f"ref_state_dict_shapes_{ucfg_name}.json"), "w") as f:
+                json.dump(shapes, f, indent=0)
+        del pipe, out
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or ["tiny8", "tiny16"])
