@@ -1,0 +1,116 @@
+/*
+ * motionclone_b200 — C ABI of the B200 (sm_100a) kernels behind MotionClone's guided denoising path.
+ *
+ * The reference (LPengYang/MotionClone) has no FFI: its "operator API" is a Python method surface executed by ATen /
+ * cuBLAS / xformers kernels. These entry points are what a binding for that surface calls; each one
+ * cites the reference lines whose arithmetic it replaces (paths relative to /root/reference/motionclone/).
+ *
+ * Conventions (all entry points):
+ *   - plain C types only: device pointers, sizes, ELEMENT strides, fp32 scalars, the CUDA stream as void*;
+ *   - enqueue-only: no allocation, no synchronisation, no global state except the error string and a launch counter;
+ *   - return 0 on success, a negative MC_E_* code otherwise (mc_last_error() has the text); the Python wrapper raises;
+ *   - fp16 storage ("half" = IEEE binary16), fp32 accumulation; index tensors are uint8.
+ *
+ * Temporal layout. A temporal tensor X (q, k, v, o, gradients) holds element (b, f, p, c) — batch, frame, spatial
+ * position, channel — at  X + b*stride_b + f*stride_f + p*stride_p + c  (channels contiguous, c = h*DH + e).
+ * The reference's "(b f) d c -> (b d) f c" rearranges (models/motion_module.py:279, :343) and head splits
+ * (models/attention.py:367-379) are therefore never materialised: they are strides.
+ * Per-row outputs (probabilities, top-1, gathered probabilities) use the reference's own order
+ * [(b d), heads, f(query), f(key)] (utils/motionclone_functions.py:280).
+ */
+#ifndef MOTIONCLONE_B200_H_
+#define MOTIONCLONE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_ABI_VERSION 1
+
+#define MC_OK 0
+#define MC_E_INVALID (-1)     /* bad argument (null pointer, unsupported shape, misaligned stride) */
+#define MC_E_UNSUPPORTED (-2) /* shape outside the compiled instantiations (L, head dim) */
+#define MC_E_CUDA (-3)        /* launch failed; mc_last_error() carries cudaGetErrorString */
+
+typedef struct mc_temporal_layout {
+  int64_t stride_b, stride_f, stride_p; /* in elements; channel stride is 1 */
+} mc_temporal_layout;
+
+/* library identity / diagnostics */
+int mc_abi_version(void);
+const char* mc_last_error(void);
+/* number of kernels this library has enqueued since load / since the last reset (bench.py "gpu_launches") */
+uint64_t mc_launch_count(void);
+void mc_reset_launch_count(void);
+
+/*
+ * Fused temporal self-attention forward: O = softmax(scale * Q K^T) V over the frame axis for every
+ * (batch, position, head). Replaces VersatileAttention's core, models/motion_module.py:309-332 ->
+ * models/attention.py:461-490 (baddbmm -> softmax -> bmm, scores and probabilities rounded to fp16 as there),
+ * and optionally, from the same tile,
+ *   probs      [B*D, H, L, L] fp16 : get_attention_scores, models/attention.py:564-611 (utils/motionclone_functions.py:279)
+ *   top_val/top_idx [B*D, H, L]    : torch.topk(k=1) + uint8 cast, utils/motionclone_functions.py:79 (ties: lowest index)
+ *   gathered   [B*D, H, L] fp16    : torch.gather(P, idx_ref), utils/motionclone_functions.py:91-92
+ * Any of o, probs, top_val/top_idx, gather_idx/gathered may be NULL (v may be NULL iff o is NULL).
+ * L in {8, 16, 32} (positional encoding max_len is 32, models/motion_module.py:60); DH in {8,16,32,40,64,80,128,160}.
+ */
+int mc_temporal_attn_fwd(const void* q, const void* k, const void* v, mc_temporal_layout qkv_layout,
+                         void* o, mc_temporal_layout o_layout,
+                         void* probs, void* top_val, uint8_t* top_idx,
+                         const uint8_t* gather_idx, void* gathered,
+                         int B, int D, int L, int H, int DH, float scale, void* stream);
+
+/*
+ * Backward of the above w.r.t. q, k, v (autograd of models/attention.py:461-490 plus the probability branch of
+ * utils/motionclone_functions.py:260-283 that torch.autograd.grad traverses at :236). Probabilities are recomputed.
+ * Incoming gradients, all optional (NULL):
+ *   d_o        : gradient of O (layout do_layout)
+ *   d_probs    : dense gradient of probs [B*D, H, L, L] fp16
+ *   gather_idx + d_gathered [B*D, H, L] : one-hot gradient of the gathered probabilities (closed form of
+ *                gather + mse_loss backward, utils/motionclone_functions.py:92-96)
+ * Outputs dq, dk (and dv unless NULL) share g_layout.
+ */
+int mc_temporal_attn_bwd(const void* q, const void* k, const void* v, mc_temporal_layout qkv_layout,
+                         const void* d_o, mc_temporal_layout do_layout,
+                         const void* d_probs, const uint8_t* gather_idx, const void* d_gathered,
+                         void* dq, void* dk, void* dv, mc_temporal_layout g_layout,
+                         int B, int D, int L, int H, int DH, float scale, void* stream);
+
+/* torch.topk(k=1, dim=-1) over fp16 rows of length L (utils/motionclone_functions.py:79); rows = product of the
+ * leading dims. Stand-alone form of the fused epilogue above. */
+int mc_top1_rows(const void* probs, int64_t rows, int L, void* top_val, uint8_t* top_idx, void* stream);
+
+/*
+ * Motion-guidance loss (utils/motionclone_functions.py:85-100) on gathered probabilities:
+ *   loss_per_module[m] = fp16( mean_i fp16(fp16(cur_m[i] - ref_m[i])^2) ),  loss_total = fp16(sum_m loss_per_module[m])
+ * (the rounding sequence of F.mse_loss on half tensors followed by stack().sum()). M <= 16 modules.
+ */
+int mc_motion_loss_fwd(int M, const void* const* cur, const void* const* ref, const int64_t* n,
+                       void* loss_per_module, void* loss_total, void* stream);
+/* d cur_m[i] = g * 2 (cur_m[i] - ref_m[i]) / n_m, with g read from device memory (fp16 scalar, no host sync). */
+int mc_motion_loss_bwd(int M, const void* const* cur, const void* const* ref, const int64_t* n,
+                       const void* d_loss_total, void* const* d_cur, void* stream);
+
+/*
+ * CFG combine + score-guided DDIM update in one pass (utils/motionclone_functions.py:239/:255 and :339-389, eta = 0,
+ * epsilon prediction), replicating the eager fp16 rounding sequence op by op:
+ *   d=h(ec-eu); m=h(cfg*d); e=h(ec+m); t1=h(sb*e); t2=h(x-t1); x0=h(t2*inv_sa);
+ *   [g2=h(sc*score); e2=h(e-g2)] ; dir=h(c*e2); t3=h(sap*x0); x_prev=h(t3+dir)
+ * sb=sqrt(1-a_t), inv_sa=1/sqrt(a_t), sap=sqrt(a_prev), c=sqrt(1-a_prev), sc=guidance_scale*sqrt(1-a_t) (fp32).
+ * score may be NULL (plain step); eps_uncond may be NULL (eps_cond then IS the combined eps, as in the reference's
+ * customized_step(model_output, ...) signature). n = element count.
+ */
+int mc_cfg_ddim_step(const void* eps_cond, const void* eps_uncond, const void* x, const void* score, void* x_prev,
+                     int64_t n, float cfg_scale, float sqrt_beta_t, float inv_sqrt_alpha_t, float sqrt_alpha_prev,
+                     float dir_coef, float score_coef, void* stream);
+
+/* add_noise, utils/motionclone_functions.py:19-23: out = h(h(sa*x0) + h(sb*noise)). */
+int mc_add_noise(const void* x0, const void* noise, void* out, int64_t n, float sqrt_alpha, float sqrt_one_minus_alpha,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOTIONCLONE_B200_H_ */

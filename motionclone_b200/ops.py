@@ -1,0 +1,251 @@
+"""Python operators over the C ABI (include/motionclone_b200.h): tensors in, tensors out, autograd where the
+reference's torch.autograd.grad (utils/motionclone_functions.py:236) must keep working. CUDA fp16 only — anything
+else raises; there is no eager fallback."""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import TemporalLayout
+
+Tensor = torch.Tensor
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require(t: Tensor, name: str, dtype=torch.float16) -> None:
+    if not t.is_cuda or t.dtype != dtype:
+        raise TypeError(f"{name}: expected a CUDA {dtype} tensor, got {t.device} {t.dtype} "
+                        "(motionclone_b200 kernels have no CPU / fp32 path)")
+
+
+def _layout_bfpc(t: Tensor) -> TemporalLayout:
+    """t is a [B, F, P, C] view (any strides, C contiguous)."""
+    if t.dim() != 4 or t.stride(3) != 1:
+        raise ValueError("temporal tensor must be a [B, F, P, C] view with contiguous channels")
+    return TemporalLayout(t.stride(0), t.stride(1), t.stride(2))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# temporal attention
+# ----------------------------------------------------------------------------------------------------------------
+def temporal_attention_forward(q: Tensor, k: Tensor, v: Optional[Tensor], heads: int, scale: float, *,
+                               want_o: bool = True, want_probs: bool = False, want_top1: bool = False,
+                               gather_idx: Optional[Tensor] = None):
+    """q, k, v: [B, F, P, C] views sharing one stride pattern (e.g. slices of a fused QKV buffer).
+
+    Returns (o [B,F,P,C] contiguous | None, probs [B*P,H,F,F] | None, (top_val, top_idx) [B*P,H,F,1] | None,
+             gathered [B*P,H,F,1] | None) — per-row outputs in the reference's order (motionclone_functions.py:280).
+    """
+    _require(q, "q"), _require(k, "k")
+    B, F, P, C = q.shape
+    if C % heads:
+        raise ValueError("channels not divisible by heads")
+    lay = _layout_bfpc(q)
+    for name, t in (("k", k), ("v", v)):
+        if t is not None and (t.shape != q.shape or t.stride() != q.stride()):
+            raise ValueError(f"{name} must share q's shape and strides")
+    o = torch.empty((B, F, P, C), dtype=q.dtype, device=q.device) if want_o else None
+    if want_o:
+        _require(v, "v")
+    rows = (B * P, heads, F)
+    probs = torch.empty(rows + (F,), dtype=q.dtype, device=q.device) if want_probs else None
+    tv = torch.empty(rows + (1,), dtype=q.dtype, device=q.device) if want_top1 else None
+    ti = torch.empty(rows + (1,), dtype=torch.uint8, device=q.device) if want_top1 else None
+    gathered = None
+    if gather_idx is not None:
+        _require(gather_idx, "gather_idx", torch.uint8)
+        if gather_idx.numel() != B * P * heads * F or not gather_idx.is_contiguous():
+            raise ValueError("gather_idx must be a contiguous uint8 [B*P, H, F, 1] tensor")
+        gathered = torch.empty(rows + (1,), dtype=q.dtype, device=q.device)
+    st = _lib.lib().mc_temporal_attn_fwd(_ptr(q), _ptr(k), _ptr(v if want_o else None), lay,
+                                         _ptr(o), _layout_bfpc(o) if want_o else TemporalLayout(0, 0, 0),
+                                         _ptr(probs), _ptr(tv), _ptr(ti), _ptr(gather_idx), _ptr(gathered),
+                                         B, P, F, heads, C // heads, float(scale), _stream())
+    _lib.check(st, "mc_temporal_attn_fwd")
+    return o, probs, ((tv, ti) if want_top1 else None), gathered
+
+
+def temporal_attention_backward(q: Tensor, k: Tensor, v: Optional[Tensor], heads: int, scale: float,
+                                d_o: Optional[Tensor], d_probs: Optional[Tensor], gather_idx: Optional[Tensor],
+                                d_gathered: Optional[Tensor], need_dv: bool = True):
+    B, F, P, C = q.shape
+    lay = _layout_bfpc(q)
+    if d_o is not None:
+        _require(d_o, "d_o")
+        if d_o.stride(3) != 1:
+            d_o = d_o.contiguous()
+    if d_probs is not None:
+        d_probs = d_probs.contiguous()
+    if d_gathered is not None:
+        d_gathered = d_gathered.contiguous()
+    dq = torch.empty((B, F, P, C), dtype=q.dtype, device=q.device)
+    dk = torch.empty_like(dq)
+    dv = torch.empty_like(dq) if (need_dv and d_o is not None) else None
+    st = _lib.lib().mc_temporal_attn_bwd(_ptr(q), _ptr(k), _ptr(v), lay,
+                                         _ptr(d_o), _layout_bfpc(d_o) if d_o is not None else TemporalLayout(0, 0, 0),
+                                         _ptr(d_probs), _ptr(gather_idx), _ptr(d_gathered),
+                                         _ptr(dq), _ptr(dk), _ptr(dv), _layout_bfpc(dq),
+                                         B, P, F, heads, C // heads, float(scale), _stream())
+    _lib.check(st, "mc_temporal_attn_bwd")
+    return dq, dk, dv
+
+
+class TemporalAttention(torch.autograd.Function):
+    """o, probs, gathered = f(q, k, v); any of the three outputs can be switched off.
+
+    Backward recomputes the probabilities in-kernel and sums the three incoming gradient branches before the softmax
+    backward (the reference builds them as separate autograd branches off the same q, k:
+    models/attention.py:461-490 for o and :564-611 via utils/motionclone_functions.py:279 for the probabilities).
+    """
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads: int, scale: float, want_probs: bool, gather_idx):
+        o, probs, _, gathered = temporal_attention_forward(q, k, v, heads, scale, want_o=True, want_probs=want_probs,
+                                                           gather_idx=gather_idx)
+        ctx.save_for_backward(q, k, v, gather_idx)
+        ctx.heads, ctx.scale = heads, scale
+        outs = (o, probs if probs is not None else q.new_empty(0), gathered if gathered is not None else q.new_empty(0))
+        ctx.mark_non_differentiable(*[t for t, used in ((outs[1], want_probs), (outs[2], gather_idx is not None))
+                                      if not used])
+        return outs
+
+    @staticmethod
+    def backward(ctx, d_o, d_probs, d_gathered):
+        q, k, v, gather_idx = ctx.saved_tensors
+        if d_probs is not None and d_probs.numel() == 0:
+            d_probs = None
+        if d_gathered is not None and d_gathered.numel() == 0:
+            d_gathered = None
+        dq, dk, dv = temporal_attention_backward(q, k, v, ctx.heads, ctx.scale, d_o, d_probs,
+                                                 gather_idx if d_gathered is not None else None, d_gathered,
+                                                 need_dv=ctx.needs_input_grad[2])
+        if dv is None and ctx.needs_input_grad[2]:
+            dv = torch.zeros_like(q)
+        return dq, dk, dv, None, None, None, None
+
+
+class TemporalProbs(torch.autograd.Function):
+    """probs = softmax(scale q k^T) only (get_attention_scores, models/attention.py:564-611), differentiable."""
+
+    @staticmethod
+    def forward(ctx, q, k, heads: int, scale: float):
+        _, probs, _, _ = temporal_attention_forward(q, k, None, heads, scale, want_o=False, want_probs=True)
+        ctx.save_for_backward(q, k)
+        ctx.heads, ctx.scale = heads, scale
+        return probs
+
+    @staticmethod
+    def backward(ctx, d_probs):
+        q, k = ctx.saved_tensors
+        dq, dk, _ = temporal_attention_backward(q, k, None, ctx.heads, ctx.scale, None, d_probs, None, None)
+        return dq, dk, None, None
+
+
+def top1_rows(probs: Tensor) -> Tuple[Tensor, Tensor]:
+    """torch.topk(probs, k=1, dim=-1) -> (values, uint8 indices), lowest index on ties (motionclone_functions.py:79)."""
+    _require(probs, "probs")
+    probs = probs.contiguous()
+    L = probs.shape[-1]
+    rows = probs.numel() // L
+    val = torch.empty(probs.shape[:-1] + (1,), dtype=probs.dtype, device=probs.device)
+    idx = torch.empty(probs.shape[:-1] + (1,), dtype=torch.uint8, device=probs.device)
+    _lib.check(_lib.lib().mc_top1_rows(_ptr(probs), rows, L, _ptr(val), _ptr(idx), _stream()), "mc_top1_rows")
+    return val, idx
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# motion loss on gathered probabilities
+# ----------------------------------------------------------------------------------------------------------------
+def _ptr_array(ts: Sequence[Tensor]):
+    arr = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    return arr
+
+
+class MotionLoss(torch.autograd.Function):
+    """sum_m mse(cur_m, ref_m) with F.mse_loss's fp16 rounding sequence (utils/motionclone_functions.py:96-100)."""
+
+    @staticmethod
+    def forward(ctx, n_modules: int, *tensors):
+        cur = [t.contiguous() for t in tensors[:n_modules]]
+        ref = [t.contiguous() for t in tensors[n_modules:]]
+        for t in cur + ref:
+            _require(t, "motion loss operand")
+        n = (ctypes.c_int64 * n_modules)(*[t.numel() for t in cur])
+        per = torch.empty(n_modules, dtype=torch.float16, device=cur[0].device)
+        total = torch.empty((), dtype=torch.float16, device=cur[0].device)
+        st = _lib.lib().mc_motion_loss_fwd(n_modules, _ptr_array(cur), _ptr_array(ref), n, _ptr(per), _ptr(total),
+                                           _stream())
+        _lib.check(st, "mc_motion_loss_fwd")
+        ctx.save_for_backward(*cur, *ref)
+        ctx.n_modules = n_modules
+        ctx.shapes = [t.shape for t in tensors[:n_modules]]
+        return total
+
+    @staticmethod
+    def backward(ctx, g):
+        M = ctx.n_modules
+        saved = ctx.saved_tensors
+        cur, ref = list(saved[:M]), list(saved[M:])
+        d = [torch.empty_like(t) for t in cur]
+        n = (ctypes.c_int64 * M)(*[t.numel() for t in cur])
+        g = g.to(torch.float16).contiguous()
+        st = _lib.lib().mc_motion_loss_bwd(M, _ptr_array(cur), _ptr_array(ref), n, _ptr(g), _ptr_array(d), _stream())
+        _lib.check(st, "mc_motion_loss_bwd")
+        return (None, *[x.view(s) for x, s in zip(d, ctx.shapes)], *([None] * M))
+
+
+def motion_loss(cur: List[Tensor], ref: List[Tensor]) -> Tensor:
+    return MotionLoss.apply(len(cur), *cur, *ref)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CFG + DDIM, add_noise
+# ----------------------------------------------------------------------------------------------------------------
+def cfg_ddim_step(eps_cond: Tensor, eps_uncond: Optional[Tensor], x: Tensor, score: Optional[Tensor], cfg_scale: float,
+                  alpha_t: Tensor, alpha_prev: Tensor, guidance_scale: float = 1.0) -> Tensor:
+    """One fused launch for motionclone_functions.py:239 + :339-389. alpha_* are 0-dim fp32 CPU tensors taken from
+    alphas_cumprod on the host (no device sync); the scalar algebra is done in fp32 torch ops exactly as the
+    reference does it (`beta_prod_t ** 0.5` etc.), so the coefficients are bit-identical."""
+    for name, t in (("eps_cond", eps_cond), ("x", x)):
+        _require(t, name)
+    eps_cond, x = eps_cond.contiguous(), x.contiguous()
+    if eps_uncond is not None:
+        _require(eps_uncond, "eps_uncond")
+        eps_uncond = eps_uncond.contiguous()
+    if score is not None:
+        _require(score, "score")
+        score = score.contiguous()
+    a_t = alpha_t.detach().to(torch.float32).cpu()
+    a_p = alpha_prev.detach().to(torch.float32).cpu()
+    sb = float((1 - a_t) ** 0.5)
+    inv_sa = float(1.0 / (a_t ** 0.5))
+    sap = float(a_p ** 0.5)
+    c = float((1 - a_p - 0.0) ** 0.5)
+    sc = float(guidance_scale * (1 - a_t) ** 0.5)
+    out = torch.empty_like(x)
+    st = _lib.lib().mc_cfg_ddim_step(_ptr(eps_cond), _ptr(eps_uncond), _ptr(x), _ptr(score), _ptr(out), x.numel(),
+                                     float(cfg_scale), sb, inv_sa, sap, c, sc, _stream())
+    _lib.check(st, "mc_cfg_ddim_step")
+    return out
+
+
+def add_noise(x0: Tensor, noise: Tensor, alpha_t: Tensor) -> Tensor:
+    """motionclone_functions.py:19-23."""
+    _require(x0, "x0"), _require(noise, "noise")
+    x0, noise = x0.contiguous(), noise.contiguous()
+    a = alpha_t.detach().to(torch.float32).cpu()
+    out = torch.empty_like(x0)
+    st = _lib.lib().mc_add_noise(_ptr(x0), _ptr(noise), _ptr(out), x0.numel(), float(a ** 0.5), float((1 - a) ** 0.5),
+                                 _stream())
+    _lib.check(st, "mc_add_noise")
+    return out

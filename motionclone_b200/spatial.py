@@ -1,0 +1,267 @@
+"""Per-frame spatial transformer (self-attention + text cross-attention + GEGLU feed-forward), token-major.
+
+Interface and state-dict keys follow the reference's motionclone/models/attention.py: Transformer3DModel (:31),
+BasicTransformerBlock (:145), CrossAttention (:302), plus diffusers-0.16's FeedForward/GEGLU that the reference
+imports (:14; keys ff.net.0.proj.*, ff.net.2.*).
+
+Design differences (B200-first):
+* tokens `[(b f), h*w, C]` are a zero-copy view of the channels_last activation; proj_in/proj_out (1x1 convs in the
+  checkpoint, `use_linear_projection=False`) run as GEMMs on that view;
+* self-attention projects q,k,v with one GEMM; cross-attention projects the text K/V ONCE per prompt, not once per
+  frame (the reference repeats the text f times, attention.py:100, and re-projects it for every frame);
+* the softmax(QK^T)V core at the reference's xformers seam (`_memory_efficient_attention_xformers`, :535-542) is
+  dispatched to `F.scaled_dot_product_attention` (flash kernels, LIBRARY code, same published semantics as
+  xformers.ops.memory_efficient_attention). The hand-written tcgen05 replacement for this seam is the next §8 row;
+  it is not claimed as this package's kernel.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+class GEGLU(nn.Module):
+    """diffusers 0.16 GEGLU: Linear(d, 2*inner) -> h * gelu_erf(gate)."""
+
+    def __init__(self, dim_in: int, dim_out: int):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        h, gate = self.proj(x).chunk(2, dim=-1)
+        return h * F.gelu(gate)
+
+
+class FeedForward(nn.Module):
+    """diffusers 0.16 FeedForward(activation_fn='geglu'): net = [GEGLU, Dropout, Linear]."""
+
+    def __init__(self, dim: int, dim_out: Optional[int] = None, mult: int = 4, dropout: float = 0.0,
+                 activation_fn: str = "geglu"):
+        super().__init__()
+        if activation_fn != "geglu":
+            raise NotImplementedError("the reference only instantiates geglu (attention.py:211, motion_module.py:209)")
+        inner = int(dim * mult)
+        self.net = nn.ModuleList([GEGLU(dim, inner), nn.Dropout(dropout), nn.Linear(inner, dim_out or dim)])
+
+    def forward(self, x):
+        for m in self.net:
+            x = m(x)
+        return x
+
+
+class CrossAttention(nn.Module):
+    """attention.py:302-611. Same parameters / attributes; `forward` keeps the reference signature."""
+
+    def __init__(self, query_dim: int, cross_attention_dim: Optional[int] = None, heads: int = 8, dim_head: int = 64,
+                 dropout: float = 0.0, bias=False, upcast_attention: bool = False, upcast_softmax: bool = False,
+                 added_kv_proj_dim: Optional[int] = None, norm_num_groups: Optional[int] = None):
+        super().__init__()
+        inner_dim = dim_head * heads
+        self.is_self = cross_attention_dim is None
+        cross_attention_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
+        if upcast_attention or upcast_softmax or added_kv_proj_dim is not None or norm_num_groups is not None:
+            raise NotImplementedError("upcast / added_kv / group_norm variants are dead in every shipped config")
+        self.upcast_attention, self.upcast_softmax = upcast_attention, upcast_softmax
+        self.scale = dim_head ** -0.5
+        self.heads = heads
+        self.sliceable_head_dim = heads
+        self._slice_size = None
+        self._use_memory_efficient_attention_xformers = True  # the fused core is always on; flag kept for API parity
+        self.added_kv_proj_dim = added_kv_proj_dim
+        self.processor = None
+        self.group_norm = None
+        self.to_q = nn.Linear(query_dim, inner_dim, bias=bias)
+        self.to_k = nn.Linear(cross_attention_dim, inner_dim, bias=bias)
+        self.to_v = nn.Linear(cross_attention_dim, inner_dim, bias=bias)
+        self.to_out = nn.ModuleList([nn.Linear(inner_dim, query_dim), nn.Dropout(dropout)])
+        self._fused = None
+
+    # ---- reference helpers kept for drop-in use (attention.py:367-385, :544-562) ----
+    def reshape_heads_to_batch_dim(self, tensor):
+        b, s, d = tensor.shape
+        h = self.heads
+        return tensor.reshape(b, s, h, d // h).permute(0, 2, 1, 3).reshape(b * h, s, d // h)
+
+    def reshape_batch_dim_to_heads(self, tensor):
+        b, s, d = tensor.shape
+        h = self.heads
+        return tensor.reshape(b // h, h, s, d).permute(0, 2, 1, 3).reshape(b // h, s, d * h)
+
+    def set_attention_slice(self, slice_size):
+        if slice_size is not None and slice_size > self.sliceable_head_dim:
+            raise ValueError(f"slice_size {slice_size} has to be smaller or equal to {self.sliceable_head_dim}.")
+        self._slice_size = slice_size  # accepted, unused: the fused cores never materialise the score matrix
+
+    def set_processor(self, processor) -> None:
+        self.processor = processor
+
+    def fused_qkv_weight(self) -> torch.Tensor:
+        """[3C, C] concatenation of to_q/to_k/to_v, rebuilt if any of them was replaced or moved (weights are frozen
+        on this path: t2v_video_sample.py:67-68)."""
+        ws = (self.to_q.weight, self.to_k.weight, self.to_v.weight)
+        key = tuple((w.data_ptr(), w._version, w.dtype, w.device) for w in ws)
+        if self._fused is None or self._fused[0] != key:
+            self._fused = (key, torch.cat([w.detach() for w in ws], dim=0).contiguous())
+        return self._fused[1]
+
+    def get_attention_scores(self, query, key, attention_mask=None):
+        """attention.py:564-611: query/key `[B*heads, S, dh]` -> probabilities in the input dtype. For temporal
+        modules (S = frames) this runs on the fused kernel; spatial sizes use the baddbmm/softmax statement."""
+        if attention_mask is not None:
+            raise NotImplementedError
+        bh, s, dh = query.shape
+        if s in (8, 16, 32) and key.shape[1] == s and query.is_cuda:
+            from . import ops
+            h = self.heads
+            to_bfpc = lambda t: t.reshape(bh // h, h, s, dh).permute(0, 2, 1, 3).reshape(1, bh // h, s, h * dh) \
+                .permute(0, 2, 1, 3)  # noqa: E731  [(B h), S, dh] -> [1, S(frames), B(positions), C]
+            probs = ops.TemporalProbs.apply(to_bfpc(query).contiguous(), to_bfpc(key).contiguous(), h, self.scale)
+            return probs.reshape(bh, s, s)
+        scores = torch.baddbmm(torch.empty(bh, s, key.shape[1], dtype=query.dtype, device=query.device), query,
+                               key.transpose(-1, -2), beta=0, alpha=self.scale)
+        return scores.softmax(dim=-1).to(query.dtype)
+
+    def _memory_efficient_attention_xformers(self, query, key, value, attention_mask=None):
+        """attention.py:535-542 seam: `[B*heads, S, dh]` in, `[B, S, heads*dh]` out."""
+        h = self.heads
+        bh, s, dh = query.shape
+        q4, k4, v4 = (t.reshape(bh // h, h, t.shape[1], dh) for t in (query, key, value))
+        o = F.scaled_dot_product_attention(q4, k4, v4, scale=self.scale)
+        return o.permute(0, 2, 1, 3).reshape(bh // h, s, h * dh)
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, text_batch: Optional[int] = None):
+        """hidden_states `[(b f), N, C]`. encoder_hidden_states: `[(b f), n, c]` as in the reference, or `[b, n, c]`
+        with `text_batch=b` so the text K/V are projected once per prompt."""
+        if attention_mask is not None:
+            raise NotImplementedError("no mask reaches attention on the live path (SURVEY appendix)")
+        bf, n, c = hidden_states.shape
+        h = self.heads
+        inner = self.to_q.out_features
+        dh = inner // h
+        if encoder_hidden_states is None:
+            qkv = F.linear(hidden_states, self.fused_qkv_weight()).view(bf, n, 3, h, dh)
+            q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))  # [(b f), h, N, dh] strided views
+            if self.processor is not None:
+                self.processor.record_qkv(self, hidden_states, qkv[:, :, 0].reshape(bf, n, inner),
+                                          qkv[:, :, 1].reshape(bf, n, inner), qkv[:, :, 2].reshape(bf, n, inner), None)
+            o = F.scaled_dot_product_attention(q, k, v, scale=self.scale)  # library flash kernel at the xformers seam
+            o = o.transpose(1, 2).reshape(bf, n, inner)
+        else:
+            ctx = encoder_hidden_states
+            b = ctx.shape[0]
+            if bf % b:
+                raise ValueError("encoder_hidden_states batch must divide the frame batch")
+            f = bf // b
+            q = self.to_q(hidden_states).view(b, f * n, h, dh).transpose(1, 2)        # frames of one prompt share K/V
+            k = self.to_k(ctx).view(b, -1, h, dh).transpose(1, 2)
+            v = self.to_v(ctx).view(b, -1, h, dh).transpose(1, 2)
+            o = F.scaled_dot_product_attention(q, k, v, scale=self.scale)
+            o = o.transpose(1, 2).reshape(bf, n, inner)
+        return self.to_out[1](self.to_out[0](o))
+
+
+class BasicTransformerBlock(nn.Module):
+    """attention.py:145-300 with unet_use_cross_frame_attention = unet_use_temporal_attention = False (live config)."""
+
+    def __init__(self, dim: int, num_attention_heads: int, attention_head_dim: int, dropout=0.0,
+                 cross_attention_dim: Optional[int] = None, activation_fn: str = "geglu",
+                 num_embeds_ada_norm: Optional[int] = None, attention_bias: bool = False,
+                 only_cross_attention: bool = False, upcast_attention: bool = False,
+                 unet_use_cross_frame_attention=None, unet_use_temporal_attention=None):
+        super().__init__()
+        if num_embeds_ada_norm is not None or unet_use_cross_frame_attention or unet_use_temporal_attention \
+                or only_cross_attention:
+            raise NotImplementedError("AdaLayerNorm / SC-attention / attn_temp are never configured by the reference")
+        self.only_cross_attention = only_cross_attention
+        self.use_ada_layer_norm = False
+        self.unet_use_cross_frame_attention = unet_use_cross_frame_attention
+        self.unet_use_temporal_attention = unet_use_temporal_attention
+        self.attn1 = CrossAttention(query_dim=dim, heads=num_attention_heads, dim_head=attention_head_dim,
+                                    dropout=dropout, bias=attention_bias, upcast_attention=upcast_attention)
+        self.norm1 = nn.LayerNorm(dim)
+        if cross_attention_dim is not None:
+            self.attn2 = CrossAttention(query_dim=dim, cross_attention_dim=cross_attention_dim,
+                                        heads=num_attention_heads, dim_head=attention_head_dim, dropout=dropout,
+                                        bias=attention_bias, upcast_attention=upcast_attention)
+            self.norm2 = nn.LayerNorm(dim)
+        else:
+            self.attn2 = self.norm2 = None
+        self.ff = FeedForward(dim, dropout=dropout, activation_fn=activation_fn)
+        self.norm3 = nn.LayerNorm(dim)
+
+    def set_use_memory_efficient_attention_xformers(self, use: bool, op=None):
+        self.attn1._use_memory_efficient_attention_xformers = use
+        if self.attn2 is not None:
+            self.attn2._use_memory_efficient_attention_xformers = use
+
+    def forward(self, hidden_states, encoder_hidden_states=None, timestep=None, attention_mask=None, video_length=None):
+        hidden_states = self.attn1(self.norm1(hidden_states), attention_mask=attention_mask) + hidden_states
+        if self.attn2 is not None:
+            hidden_states = self.attn2(self.norm2(hidden_states), encoder_hidden_states=encoder_hidden_states,
+                                       attention_mask=attention_mask) + hidden_states
+        return self.ff(self.norm3(hidden_states)) + hidden_states
+
+
+class Transformer3DModelOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+
+class Transformer3DModel(nn.Module):
+    """attention.py:31-142. 5-D `[b, c, f, h, w]` (reference convention) or internal 4-D NHWC `[(b f), c, h, w]`."""
+
+    def __init__(self, num_attention_heads: int = 16, attention_head_dim: int = 88, in_channels: Optional[int] = None,
+                 num_layers: int = 1, dropout: float = 0.0, norm_num_groups: int = 32,
+                 cross_attention_dim: Optional[int] = None, attention_bias: bool = False, activation_fn: str = "geglu",
+                 num_embeds_ada_norm: Optional[int] = None, use_linear_projection: bool = False,
+                 only_cross_attention: bool = False, upcast_attention: bool = False,
+                 unet_use_cross_frame_attention=None, unet_use_temporal_attention=None):
+        super().__init__()
+        self.use_linear_projection = use_linear_projection
+        self.num_attention_heads = num_attention_heads
+        self.attention_head_dim = attention_head_dim
+        inner_dim = num_attention_heads * attention_head_dim
+        self.in_channels = in_channels
+        self.norm = nn.GroupNorm(num_groups=norm_num_groups, num_channels=in_channels, eps=1e-6, affine=True)
+        if use_linear_projection:
+            self.proj_in = nn.Linear(in_channels, inner_dim)
+            self.proj_out = nn.Linear(in_channels, inner_dim)
+        else:
+            self.proj_in = nn.Conv2d(in_channels, inner_dim, kernel_size=1, stride=1, padding=0)
+            self.proj_out = nn.Conv2d(inner_dim, in_channels, kernel_size=1, stride=1, padding=0)
+        self.transformer_blocks = nn.ModuleList([
+            BasicTransformerBlock(inner_dim, num_attention_heads, attention_head_dim, dropout=dropout,
+                                  cross_attention_dim=cross_attention_dim, activation_fn=activation_fn,
+                                  num_embeds_ada_norm=num_embeds_ada_norm, attention_bias=attention_bias,
+                                  only_cross_attention=only_cross_attention, upcast_attention=upcast_attention,
+                                  unet_use_cross_frame_attention=unet_use_cross_frame_attention,
+                                  unet_use_temporal_attention=unet_use_temporal_attention)
+            for _ in range(num_layers)])
+
+    @staticmethod
+    def _as_linear(conv_or_linear, t):
+        w = conv_or_linear.weight
+        return F.linear(t, w.reshape(w.shape[0], w.shape[1]), conv_or_linear.bias)
+
+    def forward(self, hidden_states, encoder_hidden_states=None, timestep=None, return_dict: bool = True,
+                video_length: Optional[int] = None):
+        five_d = hidden_states.dim() == 5
+        if five_d:
+            b, c, f, h, w = hidden_states.shape
+            video_length = f
+            hidden_states = hidden_states.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+        n, c, h, w = hidden_states.shape
+        residual = hidden_states
+        t = self.norm(hidden_states).permute(0, 2, 3, 1).reshape(n, h * w, c)
+        t = self._as_linear(self.proj_in, t)
+        for block in self.transformer_blocks:
+            # encoder_hidden_states stays [b, 77, c]: K/V are projected once per prompt, not per frame
+            t = block(t, encoder_hidden_states=encoder_hidden_states, timestep=timestep, video_length=video_length)
+        t = self._as_linear(self.proj_out, t)
+        out = t.reshape(n, h, w, -1).permute(0, 3, 1, 2) + residual
+        if five_d:
+            out = out.reshape(b, f, c, h, w).permute(0, 2, 1, 3, 4)
+        return Transformer3DModelOutput(out) if return_dict else (out,)

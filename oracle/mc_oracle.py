@@ -95,6 +95,27 @@ def ddim_guided_step(eps: Tensor, x: Tensor, score: Optional[Tensor], a_t: Tenso
     return a_prev ** 0.5 * x0 + direction
 
 
+def cfg_ddim_step_fp16_sequence(eps_cond: Tensor, eps_uncond: Tensor, x: Tensor, score: Optional[Tensor],
+                                cfg_scale: float, a_t: Tensor, a_prev: Tensor, guidance_scale: float = 1.0) -> Tensor:
+    """What the reference's eager CUDA ops compute for fp16 tensors at utils/motionclone_functions.py:239 + :339-389,
+    restated on fp32 values with an explicit fp16 rounding after every op. On CUDA a 0-dim
+    fp32 CPU operand stays fp32 (opmath) and `tensor / cpu_scalar` multiplies by the fp32 reciprocal; CPU eager half
+    ops instead cast the 0-dim operand to fp16 first, so `ddim_guided_step` on CPU half tensors is NOT this sequence.
+    """
+    h = lambda t: t.to(torch.float16).to(torch.float32)  # noqa: E731
+    a_t = a_t.to(torch.float32).cpu()
+    a_prev = a_prev.to(torch.float32).cpu()
+    sb, inv_sa = (1 - a_t) ** 0.5, 1.0 / (a_t ** 0.5)
+    sap, c = a_prev ** 0.5, (1 - a_prev - 0.0) ** 0.5
+    ec, eu, xf = eps_cond.float(), eps_uncond.float(), x.float()
+    e = h(ec + h(cfg_scale * h(ec - eu)))
+    x0 = h(h(xf - h(sb * e)) * inv_sa)
+    e2 = e
+    if score is not None and guidance_scale > 0.0:
+        e2 = h(e - h((guidance_scale * (1 - a_t) ** 0.5) * score.float()))
+    return h(h(sap * x0) + h(c * e2)).to(torch.float16)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # temporal attention, top-1 extraction, motion loss
 # ----------------------------------------------------------------------------------------------------------------
