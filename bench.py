@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Headline benchmark: frames/sec of MotionClone's guided denoising loop (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            this package, one process per GPU (torchrun for N > 1)
+  python bench.py --impl reference --steps K --warmup W     the reference's CPU path (oracle port) on the host cores
+
+A "step" is one sample: the latent -> latent 50-step DDIM loop (reference sample_video, motionclone_functions.py:164-167)
+at BASELINE.json configs[1]: t2v_object, 16 x 512 x 512, random-init SD1.5 + v3_sd15_mm widths, fp16. The shipped YAML
+(300 steps / 180 guided / guidance_scale 0.4) is mapped to 50 steps as BASELINE.md §4 states: 30 guided steps,
+guidance_scale 0.4, warm_up = cool_up = 10. VAE, CLIP and video I/O are excluded (synthetic latents / embeddings).
+One JSON line on stdout (rank 0); everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "frames/sec at 16x512x512 T2V, 50-step DDIM"
+UNIT = "frames/s"
+INFER = dict(cfg_scale=7.5, negative_prompt="", warm_up_steps=10, cool_up_steps=10, motion_guidance_weight=2000,
+             motion_guidance_blocks=["up_blocks.1"], add_noise_step=400, inference_steps=50, guidance_steps=30,
+             guidance_scale=0.4, video_length=16, height=512, width=512, new_prompt="synthetic")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(s[3 + j].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples),
+                "reasons": reasons}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port (oracle/mc_oracle.py) in fp32 on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(n_pairs: int, budget_s: float, infer: dict):
+    """Times guided and plain DDIM steps of the CPU oracle at the bench shapes; returns (t_guided, t_plain, info).
+    Only place bench.py executes oracle/ (task spec ④: cpu_baseline / --impl reference)."""
+    from motionclone_b200.synthetic import UNET_SD15_CONFIG, synthetic_inputs, synthetic_state_dict
+    from motionclone_b200.unet3d import UNet3DConditionModel
+    from oracle import mc_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    with torch.device("meta"):
+        shapes = {k: v.shape for k, v in UNet3DConditionModel(**UNET_SD15_CONFIG).state_dict().items()}
+    t0 = time.time()
+    sd = synthetic_state_dict(shapes, 42)
+    log(f"[cpu] fp32 weights in {time.time() - t0:.0f}s; {cores} host threads")
+    inp = synthetic_inputs(infer["video_length"], infer["height"], infer["width"], 768, 42)
+    L, hw = infer["video_length"], (infer["height"] // 32) * (infer["width"] // 32)
+    g = torch.Generator().manual_seed(0)  # a synthetic motion representation of the right shape (timing only)
+    names = [f"up_blocks.1.motion_modules.{i}.temporal_transformer.transformer_blocks.0.attention_blocks.{j}"
+             for i in range(3) for j in range(2)]
+    rep = {n: [torch.rand(hw, 8, L, 1, generator=g), torch.randint(0, L, (hw, 8, L, 1), generator=g).to(torch.uint8)]
+           for n in names}
+    timesteps = O.uneven_timesteps(infer["inference_steps"], infer["guidance_steps"], infer["guidance_scale"])
+    acp = O.alphas_cumprod()
+    lat, text = inp["noisy_latents"], inp["text_embeddings"]
+    tg, tp = [], []
+    start = time.time()
+    for i in range(n_pairs):
+        t0 = time.time()
+        O.single_step(sd, UNET_SD15_CONFIG, infer, lat, infer["guidance_steps"], timesteps, acp, text, rep)  # plain
+        tp.append(time.time() - t0)
+        log(f"[cpu] plain step {tp[-1]:.1f}s")
+        if time.time() - start > budget_s and tg:
+            break
+        t0 = time.time()
+        O.single_step(sd, UNET_SD15_CONFIG, infer, lat, 0, timesteps, acp, text, rep)  # guided (fwd, fwd+bwd)
+        tg.append(time.time() - t0)
+        log(f"[cpu] guided step {tg[-1]:.1f}s")
+        if time.time() - start > budget_s:
+            break
+    return statistics.median(tg), statistics.median(tp), dict(cores=cores, guided_steps_timed=len(tg),
+                                                               plain_steps_timed=len(tp))
+
+
+def fps_from_step_times(t_guided, t_plain, infer):
+    G, S = infer["guidance_steps"], infer["inference_steps"]
+    return infer["video_length"] / (G * t_guided + (S - G) * t_plain)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    infer = dict(INFER, inference_steps=args.ddim_steps, guidance_steps=int(round(args.ddim_steps * 0.6)))
+    n = max(1, args.steps + args.warmup)
+    # each arm "step" is a bounded sample: one guided + one plain DDIM step at the bench shapes; the first `warmup`
+    # pairs are discarded when more than one pair fits in the time budget
+    tg, tp, info = cpu_reference_steps(n, args.ref_budget, infer)
+    fps = fps_from_step_times(tg, tp, infer)
+    sample = (f"median of {info['guided_steps_timed']} guided + {info['plain_steps_timed']} plain DDIM steps at "
+              f"16x512x512 (fp32, math attention), extrapolated to {infer['inference_steps']} steps "
+              f"({infer['guidance_steps']} guided)")
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": 0, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * infer["video_length"] / fps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "t2v_object 16x512x512, 50-step DDIM (30 guided), SD1.5+mm widths, CPU oracle port"},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": sample,
+                             "s_per_guided_step": tg, "s_per_plain_step": tp},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# this package's arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_own_arm(args):
+    import motionclone_b200 as mc
+    from motionclone_b200 import _lib, dist as mcdist, ops
+    from motionclone_b200.synthetic import UNET_SD15_CONFIG, synthetic_inputs
+    import torch.distributed as tdist
+
+    rank, world, local = mcdist.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs CUDA (no CPU fallback); --impl reference is the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    infer = dict(INFER, inference_steps=args.ddim_steps, guidance_steps=int(round(args.ddim_steps * 0.6)))
+    L = infer["video_length"]
+
+    t0 = time.time()
+    pipe = mc.build_pipeline(UNET_SD15_CONFIG, infer, device=dev, weight_seed=42)
+    log(f"[rank {rank}] model built in {time.time() - t0:.0f}s")
+    # weak scaling: every rank denoises its own samples (seed 42 + global sample index) of ONE shared reference clip
+    inp = synthetic_inputs(L, infer["height"], infer["width"], 768, 42)
+    h = lambda t: t.to(dev, torch.float16)  # noqa: E731
+    pipe.set_prompt_embeds(h(inp["text_embeddings"]))
+    rep = None
+    if rank == 0:
+        pipe.input_config["video_latents"], pipe.input_config["video_noise"] = h(inp["clip_latents"]), h(inp["clip_noise"])
+        rep = pipe.obtain_motion_representation()
+    tb = time.time()
+    rep = mcdist.broadcast_representation(rep, dev)  # B1: the only collective
+    torch.cuda.synchronize()
+    bcast_ms = (time.time() - tb) * 1e3
+    pipe.motion_representation_dict, pipe.motion_representation_path = rep, None
+
+    def sample_latents(i):
+        return synthetic_inputs(L, infer["height"], infer["width"], 768, 1000 + rank + world * i)["noisy_latents"]
+
+    n_total = args.warmup + 2 * args.steps
+    host = [sample_latents(i).half().pin_memory() for i in range(n_total)]
+    resident = [t.to(dev) for t in host]
+    text_host = inp["text_embeddings"].half().pin_memory()
+    rep_buf, manifest = mcdist.pack_representation(rep)
+    rep_host = rep_buf.cpu().pin_memory()
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n, offset):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(offset + i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
+        return ms.item()
+
+    def step_resident(i):
+        pipe.sample_video(noisy_latents=resident[i], return_latents=True)
+
+    out_host = torch.empty(1, 4, L, infer["height"] // 8, infer["width"] // 8, dtype=torch.float16).pin_memory()
+
+    def step_e2e(i):  # public API with HOST buffers: H2D of latents, text, motion representation; D2H of the result
+        pipe.set_prompt_embeds(text_host.to(dev, non_blocking=True))
+        pipe.motion_representation_dict = mcdist.unpack_representation(rep_host.to(dev, non_blocking=True), manifest)
+        out = pipe.sample_video(noisy_latents=host[i], return_latents=True)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    _lib.reset_launch_count()
+    ops.TIMER = ops.KernelTimer()
+    ms = timed(step_resident, args.steps, args.warmup)
+    launches = _lib.launch_count()
+    ksum = ops.TIMER.summary()
+    ops.TIMER = None
+    ms_e2e = timed(step_e2e, args.steps, args.warmup + args.steps)
+    clk = clocks.finish()
+
+    frames = L * args.steps * world
+    value = frames / (ms / 1e3)
+    e2e = frames / (ms_e2e / 1e3)
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    n_l, n_b, n_ms = ksum.get("temporal_attn_fwd", (0, 0, 0.0))
+    achieved = (n_b / 1e9) / (n_ms / 1e3) if n_ms > 0 else None
+    roof = {"kernel": "temporal_attn_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": (achieved / peak) if achieved else None, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
+            "launches": n_l, "algorithmic_bytes_per_launch": (n_b / n_l) if n_l else None,
+            "avg_launch_us": (1e3 * n_ms / n_l) if n_l else None,
+            "l2_policy": "in situ: Q/K/V were just written by the QKV GEMM and can be L2-resident; "
+                         "profiles/ holds the cold-L2 per-shape numbers"}
+    b_l, b_b, b_ms = ksum.get("temporal_attn_bwd", (0, 0, 0.0))
+    if b_ms > 0:
+        roof["bwd"] = {"launches": b_l, "achieved": (b_b / 1e9) / (b_ms / 1e3), "frac": (b_b / 1e9) / (b_ms / 1e3) / peak}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        tg, tp, info = cpu_reference_steps(1, 1e9, infer)
+        cpu = {"value": fps_from_step_times(tg, tp, infer), "unit": UNIT, "cores": info["cores"], "kind": "port",
+               "sample": "1 guided + 1 plain DDIM step at 16x512x512 (fp32 CPU oracle, math attention), extrapolated to "
+                         f"{infer['inference_steps']} steps ({infer['guidance_steps']} guided)",
+               "s_per_guided_step": tg, "s_per_plain_step": tp}
+    lat_bytes = host[0].numel() * 2
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "t2v_object 16x512x512, 50-step DDIM (30 guided, guidance_scale 0.4), random-init "
+                                   "SD1.5 + v3_sd15_mm widths, 1 sample per step per GPU",
+                       "ddim_steps": infer["inference_steps"], "guided_steps": infer["guidance_steps"],
+                       "parallelism": f"replica x{world} (independent samples), one broadcast of the motion representation",
+                       "l2": "inputs larger than L2 (2.6 GB weights stream every UNet forward)",
+                       "broadcast_ms": bcast_ms},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": lat_bytes + text_host.numel() * 2 + rep_host.numel(),
+                    "d2h_bytes_per_step": lat_bytes, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ddim-steps", type=int, default=50, help="profiling only: anything but 50 is not a bench value")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=240.0, help="seconds of CPU work for --impl reference")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_own_arm(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -119,6 +119,7 @@ def obtain_motion_representation(self, generator=None, motion_representation_pat
         torch.save(motion_representation, motion_representation_path)  # same on-disk format as :81
     self.motion_representation_path = motion_representation_path
     self.motion_representation_dict = motion_representation
+    self._repr_source = motion_representation_path
     self._repr_on_device = None
     return motion_representation
 
@@ -188,11 +189,12 @@ def sample_video(self, eta: float = 0.0, generator=None, noisy_latents: Optional
     noisy_latents = self.prepare_latents(batch_size, self.unet.config.in_channels, _cfg_get(cfg, "video_length"),
                                          _cfg_get(cfg, "height"), _cfg_get(cfg, "width"), self.text_embeddings.dtype,
                                          device, generator, noisy_latents)
-    if getattr(self, "motion_representation_dict", None) is None or \
-            (self.motion_representation_path is not None and getattr(self, "_repr_loaded_from", None)
-             != self.motion_representation_path and not getattr(self, "_repr_in_memory", False)):
-        self.motion_representation_dict = torch.load(self.motion_representation_path)  # :154
-        self._repr_loaded_from = self.motion_representation_path
+    path = getattr(self, "motion_representation_path", None)
+    if path is not None and getattr(self, "_repr_source", None) != path:
+        self.motion_representation_dict = torch.load(path)  # :154
+        self._repr_source = path
+    elif getattr(self, "motion_representation_dict", None) is None:
+        raise ValueError("no motion representation: run obtain_motion_representation or set motion_representation_path")
     self.motion_scale = _cfg_get(cfg, "motion_guidance_weight")
     extra_step_kwargs = self.prepare_extra_step_kwargs(generator, eta)
     with self.progress_bar(total=_cfg_get(cfg, "inference_steps")) as bar:
@@ -228,7 +230,7 @@ def single_step_video(self, noisy_latents, step_index, step_t, extra_step_kwargs
             loss_motion = ((guidance_steps - step_index) / _cfg_get(cfg, "cool_up_steps")) * loss_motion
         gradient = torch.autograd.grad(loss_motion, control_latents, allow_unused=True)[0]
         assert gradient is not None, f"Step {step_index}: grad is None"
-        self.last_loss = loss_motion.detach()
+        self.last_loss, self.last_gradient = loss_motion.detach(), gradient.detach()
         _set_processor_mode(self, None)
         out = self.scheduler.customized_step_fused(eps_c.detach(), eps_u, cfg_scale, step_index,
                                                    control_latents.detach(), score=gradient.detach(),

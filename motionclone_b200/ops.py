@@ -14,6 +14,35 @@ from ._lib import TemporalLayout
 Tensor = torch.Tensor
 
 
+class KernelTimer:
+    """CUDA-event timing of this package's launches on the launching stream (bench.py's roofline leg). Installed with
+    `ops.TIMER = KernelTimer()`; `summary()` synchronises and returns {kernel: (launches, algorithmic_bytes, ms)}."""
+
+    def __init__(self):
+        self.records = []
+
+    def start(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def stop(self, name: str, nbytes: int, ev0):
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record(torch.cuda.current_stream())
+        self.records.append((name, nbytes, ev0, ev1))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, nbytes, e0, e1 in self.records:
+            n, b, ms = out.get(name, (0, 0, 0.0))
+            out[name] = (n + 1, b + nbytes, ms + e0.elapsed_time(e1))
+        return out
+
+
+TIMER: Optional[KernelTimer] = None
+
+
 def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -67,11 +96,14 @@ def temporal_attention_forward(q: Tensor, k: Tensor, v: Optional[Tensor], heads:
         if gather_idx.numel() != B * P * heads * F or not gather_idx.is_contiguous():
             raise ValueError("gather_idx must be a contiguous uint8 [B*P, H, F, 1] tensor")
         gathered = torch.empty(rows + (1,), dtype=q.dtype, device=q.device)
+    ev0 = TIMER.start() if TIMER is not None else None
     st = _lib.lib().mc_temporal_attn_fwd(_ptr(q), _ptr(k), _ptr(v if want_o else None), lay,
                                          _ptr(o), _layout_bfpc(o) if want_o else TemporalLayout(0, 0, 0),
                                          _ptr(probs), _ptr(tv), _ptr(ti), _ptr(gather_idx), _ptr(gathered),
                                          B, P, F, heads, C // heads, float(scale), _stream())
     _lib.check(st, "mc_temporal_attn_fwd")
+    if ev0 is not None:  # algorithmic bytes: Q, K, V read + O written; by-products are not counted
+        TIMER.stop("temporal_attn_fwd", (4 if want_o else 2) * B * F * P * C * 2, ev0)
     return o, probs, ((tv, ti) if want_top1 else None), gathered
 
 
@@ -91,12 +123,15 @@ def temporal_attention_backward(q: Tensor, k: Tensor, v: Optional[Tensor], heads
     dq = torch.empty((B, F, P, C), dtype=q.dtype, device=q.device)
     dk = torch.empty_like(dq)
     dv = torch.empty_like(dq) if (need_dv and d_o is not None) else None
+    ev0 = TIMER.start() if TIMER is not None else None
     st = _lib.lib().mc_temporal_attn_bwd(_ptr(q), _ptr(k), _ptr(v), lay,
                                          _ptr(d_o), _layout_bfpc(d_o) if d_o is not None else TemporalLayout(0, 0, 0),
                                          _ptr(d_probs), _ptr(gather_idx), _ptr(d_gathered),
                                          _ptr(dq), _ptr(dk), _ptr(dv), _layout_bfpc(dq),
                                          B, P, F, heads, C // heads, float(scale), _stream())
     _lib.check(st, "mc_temporal_attn_bwd")
+    if ev0 is not None:  # Q, K (V, dO) read; dQ, dK (dV) written
+        TIMER.stop("temporal_attn_bwd", (7 if d_o is not None else 4) * B * F * P * C * 2, ev0)
     return dq, dk, dv
 
 
