@@ -20,8 +20,6 @@
 
 namespace mc {
 
-constexpr int kWarps = 4;
-constexpr int kThreads = kWarps * 32;
 constexpr int kHeaderBytes = 128;
 
 template <int DH_, int L_>
@@ -63,10 +61,12 @@ struct TAParams {
 };
 
 // Byte offset (inside one staged tensor) of "virtual row" idx of an item whose first position is pl0.
-// L >= 16: idx is the frame.  L == 8: two positions are packed, idx = 8*(position in pair) + frame.
+// L >= 16: idx is the frame.  L == 8: two positions are packed, idx = 8*(position in pair) + frame; when the tile
+// holds an odd number of positions the last one is paired with itself (duplicate rows compute and store identical
+// values).
 template <int L>
 __device__ __forceinline__ uint32_t vrow_off(int idx, int pl0, const TileGeom& g) {
-  if (L == 8) return (idx & 7) * g.pitch + ((pl0 + (idx >> 3)) * g.W) * 2;
+  if (L == 8) return (idx & 7) * g.pitch + (min(pl0 + (idx >> 3), g.P - 1) * g.W) * 2;  // odd tail: pair with itself
   return idx * g.pitch + (pl0 * g.W) * 2;
 }
 
@@ -233,16 +233,17 @@ __device__ __forceinline__ void probs_to_afrag(uint32_t (&pa)[C::KK][4], const f
 
 // row bookkeeping of an item: global row index R = ((b*D + pos)*H + h)*L + frame for accumulator half hf of tile mt
 template <typename C>
-__device__ __forceinline__ int64_t out_row(int b, int p_first, int h, int mt, int gq, int hf, int D, int H) {
-  if (C::L == 8) return ((int64_t)(b * D + p_first + hf) * H + h) * 8 + gq;
+__device__ __forceinline__ int64_t out_row(int b, int p_first, int p_last, int h, int mt, int gq, int hf, int D,
+                                           int H) {
+  if (C::L == 8) return ((int64_t)(b * D + min(p_first + hf, p_last)) * H + h) * 8 + gq;
   return ((int64_t)(b * D + p_first) * H + h) * C::L + mt * 16 + gq + 8 * hf;
 }
 
 // ================================================================================================================
 // forward
 // ================================================================================================================
-template <int DH, int L>
-__global__ void __launch_bounds__(kThreads) temporal_attn_fwd_kernel(const TAParams prm) {
+template <int DH, int L, int NW>
+__global__ void __launch_bounds__(NW * 32) temporal_attn_fwd_kernel(const TAParams prm) {
   using C = TACfg<DH, L>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem);
@@ -282,12 +283,12 @@ __global__ void __launch_bounds__(kThreads) temporal_attn_fwd_kernel(const TAPar
   }
   mbar_wait(bar_qk, 0);
 
-  const int n_items = (g.P / C::PP) * g.HG;
+  const int n_items = ((g.P + C::PP - 1) / C::PP) * g.HG;
   const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(sV);
   const int gq = lane >> 2, t = lane & 3;
   bool v_ready = false;
 
-  for (int item = warp; item < n_items; item += kWarps) {
+  for (int item = warp; item < n_items; item += NW) {
     const int pl0 = (item / g.HG) * C::PP;
     const int hl = item % g.HG;
     const int colbase = hl * DH;
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kThreads) temporal_attn_fwd_kernel(const TAPar
       // ---- per-row outputs: probabilities, top-1 (lowest index on ties), gathered probability ----
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        const int64_t R = out_row<C>(b, p0 + pl0, h, mt, gq, hf, prm.D, prm.H);
+        const int64_t R = out_row<C>(b, p0 + pl0, p0 + g.P - 1, h, mt, gq, hf, prm.D, prm.H);
         if (prm.probs != nullptr) {
           __half* prow = prm.probs + R * L;
 #pragma unroll
@@ -391,8 +392,8 @@ __global__ void __launch_bounds__(kThreads) temporal_attn_fwd_kernel(const TAPar
 // backward: dq, dk, dv from d_o and/or the probability branches. Staged: Q, K, V, dO; outputs reuse dead tiles
 // (dV -> V, dQ -> dO, dK -> K).
 // ================================================================================================================
-template <int DH, int L>
-__global__ void __launch_bounds__(kThreads) temporal_attn_bwd_kernel(const TAParams prm) {
+template <int DH, int L, int NW>
+__global__ void __launch_bounds__(NW * 32) temporal_attn_bwd_kernel(const TAParams prm) {
   using C = TACfg<DH, L>;
   static_assert(C::MT == 1 || L == 32, "");
   extern __shared__ __align__(128) uint8_t smem[];
@@ -439,11 +440,11 @@ __global__ void __launch_bounds__(kThreads) temporal_attn_bwd_kernel(const TAPar
   mbar_wait(bar_qk, 0);
   if (has_do) mbar_wait(bar_v, 0);
 
-  const int n_items = (g.P / C::PP) * g.HG;
+  const int n_items = ((g.P + C::PP - 1) / C::PP) * g.HG;
   const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(sV), sDa = smem_u32(sD);
   const int gq = lane >> 2, t = lane & 3;
 
-  for (int item = warp; item < n_items; item += kWarps) {
+  for (int item = warp; item < n_items; item += NW) {
     const int pl0 = (item / g.HG) * C::PP;
     const int hl = item % g.HG;
     const int colbase = hl * DH;
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(kThreads) temporal_attn_bwd_kernel(const TAPar
       }
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        const int64_t R = out_row<C>(b, p0 + pl0, h, mt, gq, hf, prm.D, prm.H);
+        const int64_t R = out_row<C>(b, p0 + pl0, p0 + g.P - 1, h, mt, gq, hf, prm.D, prm.H);
         int gi = -1;
         float gv = 0.f;
         if (prm.d_gathered != nullptr) {
@@ -590,8 +591,7 @@ static bool choose_geom(int D, int L, int H, int DH, int ntensors, bool need_eve
   const int target = (ntensors == 3) ? 64 * 1024 : 84 * 1024;
   int HG = H;
   auto tbytes = [&](int P, int hg) { return (int64_t)ntensors * L * P * hg * DH * 2; };
-  const int Pmin = need_even_p ? 2 : 1;
-  if (D % Pmin != 0) return false;
+  const int Pmin = (need_even_p && D % 2 == 0) ? 2 : 1;  // L == 8 packs two positions per item; odd D: tail pairs with itself
   while (HG > 1 && tbytes(Pmin, HG) > target && (HG % 2 == 0)) HG /= 2;
   int P = Pmin;
   if (HG == H) {  // whole positions are contiguous runs: grow P while the tile stays small and there is enough work
@@ -618,10 +618,17 @@ static int launch_fwd(TAParams& prm, cudaStream_t st) {
     return MC_E_INVALID;
   }
   const int smem = kHeaderBytes + 3 * prm.g.tensor_bytes;
-  auto kern = temporal_attn_fwd_kernel<DH, L>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int64_t grid = (int64_t)prm.B * (prm.D / prm.g.P) * (prm.H / prm.g.HG);
-  kern<<<(unsigned)grid, kThreads, smem, st>>>(prm);
+  const int n_items = ((prm.g.P + TACfg<DH, L>::PP - 1) / TACfg<DH, L>::PP) * prm.g.HG;
+  if (n_items >= 8) {  // one (position, head) item per warp pass: more warps hide the ldmatrix -> mma -> shuffle latency
+    auto kern = temporal_attn_fwd_kernel<DH, L, 8>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kern<<<(unsigned)grid, 8 * 32, smem, st>>>(prm);
+  } else {
+    auto kern = temporal_attn_fwd_kernel<DH, L, 4>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kern<<<(unsigned)grid, 4 * 32, smem, st>>>(prm);
+  }
   count_launch();
   return check_launch("temporal_attn_fwd");
 }
@@ -633,10 +640,17 @@ static int launch_bwd(TAParams& prm, cudaStream_t st) {
     return MC_E_INVALID;
   }
   const int smem = kHeaderBytes + 4 * prm.g.tensor_bytes;
-  auto kern = temporal_attn_bwd_kernel<DH, L>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int64_t grid = (int64_t)prm.B * (prm.D / prm.g.P) * (prm.H / prm.g.HG);
-  kern<<<(unsigned)grid, kThreads, smem, st>>>(prm);
+  const int n_items = ((prm.g.P + TACfg<DH, L>::PP - 1) / TACfg<DH, L>::PP) * prm.g.HG;
+  if (n_items >= 8) {
+    auto kern = temporal_attn_bwd_kernel<DH, L, 8>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kern<<<(unsigned)grid, 8 * 32, smem, st>>>(prm);
+  } else {
+    auto kern = temporal_attn_bwd_kernel<DH, L, 4>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kern<<<(unsigned)grid, 4 * 32, smem, st>>>(prm);
+  }
   count_launch();
   return check_launch("temporal_attn_bwd");
 }

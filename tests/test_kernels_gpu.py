@@ -91,6 +91,7 @@ SHAPES = [  # (L, heads, dh, B, P)
     (16, 8, 40, 1, 64), (16, 8, 80, 2, 16), (16, 8, 160, 1, 16), (16, 8, 8, 1, 16), (16, 8, 16, 1, 4),
     (16, 2, 32, 1, 8), (16, 8, 64, 1, 8), (16, 8, 128, 1, 4),
     (8, 8, 40, 1, 64), (8, 8, 160, 2, 4), (8, 8, 8, 1, 16), (8, 8, 16, 1, 2), (8, 8, 32, 1, 16), (8, 8, 80, 1, 6),
+    (8, 8, 40, 1, 1), (8, 8, 16, 2, 3),  # odd position counts: the tail position is paired with itself
     (32, 8, 40, 1, 16), (32, 8, 160, 1, 4), (32, 8, 80, 1, 8), (32, 8, 16, 2, 4),
 ]
 
@@ -192,7 +193,7 @@ def _close(a, b, rel=2e-2, name=""):
 
 
 @pytest.mark.parametrize("L,H,DH,B,P", [(16, 8, 40, 1, 16), (16, 8, 160, 1, 4), (16, 8, 80, 2, 8), (8, 8, 40, 1, 8),
-                                        (8, 8, 16, 1, 4), (32, 8, 40, 1, 4), (32, 8, 160, 1, 2), (16, 8, 8, 1, 4)])
+                                        (8, 8, 16, 1, 4), (8, 8, 40, 1, 1), (8, 8, 16, 1, 3), (32, 8, 40, 1, 4), (32, 8, 160, 1, 2), (16, 8, 8, 1, 4)])
 @pytest.mark.parametrize("branches", ["o", "o+gather", "gather", "probs", "all"])
 def test_temporal_attention_backward(L, H, DH, B, P, branches):
     ops, dev = _ops(), _dev()

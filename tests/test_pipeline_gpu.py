@@ -53,6 +53,11 @@ def run(request):
         fwd = pipe.unet(inp["noisy_latents"].to(dev, torch.float16), 500,
                         encoder_hidden_states=inp["text_embeddings"][[1]].to(dev, torch.float16)).sample
     rep = pipe.obtain_motion_representation(motion_representation_path=None)
+    # the sampling loop is compared with the reference on the REFERENCE's motion representation (identical inputs);
+    # the package's own extraction is checked separately in test_motion_representation_vs_reference
+    pipe.motion_representation_dict = {str(n): [torch.from_numpy(g[f"repr_val_{i}"]).half(),
+                                                torch.from_numpy(g[f"repr_idx_{i}"])]
+                                       for i, n in enumerate(g["repr_names"])}
     per_step, losses, grads = [], [], {}
     step = pipe.single_step_video
 
@@ -148,7 +153,10 @@ def test_latents_vs_same_device_oracle(run):
                                             h(inp["text_embeddings"][[0]]), icfg["add_noise_step"])
     mism = sum(int((rep[n][1] != run["rep"][n][1]).sum()) for n in rep)
     tot = sum(rep[n][1].numel() for n in rep)
-    steps = O.sample_loop(sd, ucfg, icfg, h(inp["noisy_latents"]), h(inp["text_embeddings"]), rep)
+    g = run["g"]
+    gold = {str(n): [h(torch.from_numpy(g[f"repr_val_{i}"])), torch.from_numpy(g[f"repr_idx_{i}"]).to(dev)]
+            for i, n in enumerate(g["repr_names"])}
+    steps = O.sample_loop(sd, ucfg, icfg, h(inp["noisy_latents"]), h(inp["text_embeddings"]), gold)
     rels = [_rel(run["per_step"][i], steps[i].cpu()) for i in range(len(steps))]
     print(run["case"], f"vs fp16 oracle on device: index mismatches {mism}/{tot}; per-step latent rel err {rels}")
     assert mism / tot < 0.02
