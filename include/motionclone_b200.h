@@ -110,6 +110,24 @@ int mc_cfg_ddim_step(const void* eps_cond, const void* eps_uncond, const void* x
 int mc_add_noise(const void* x0, const void* noise, void* out, int64_t n, float sqrt_alpha, float sqrt_one_minus_alpha,
                  void* stream);
 
+/*
+ * Memory-bound glue of the UNet3D forward on NHWC / token-major fp16 activations (inference passes only; the
+ * autograd-carrying guided pass keeps ATen).
+ *
+ * GroupNorm over channels_last x [N, HW, C] (N = batch*frames) with G groups, optional fused SiLU: replaces
+ * InflatedGroupNorm + nonlinearity (models/resnet.py:21-29, :186-187, :197-204) and the transformer input norms
+ * (models/attention.py:61,105; models/motion_module.py:112,145). Two launches (Welford partials, then apply);
+ * workspace >= mc_groupnorm_workspace_bytes(N, G) bytes of device memory.
+ */
+int64_t mc_groupnorm_workspace_bytes(int N, int G);
+int mc_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* beta, void* workspace,
+                      int64_t workspace_bytes, int N, int HW, int C, int G, float eps, int fuse_silu, void* stream);
+/* LayerNorm over the last dim (models/attention.py:189,206,212; models/motion_module.py:204,210), C % 8 == 0, C <= 2048 */
+int mc_layernorm(const void* x, void* y, const void* gamma, const void* beta, int64_t rows, int C, float eps, void* stream);
+/* GEGLU of diffusers-0.16 FeedForward (models/attention.py:211, models/motion_module.py:209):
+ * in [T, 2I] = [h | gate] -> out [T, I] = h * gelu_erf(gate), gelu output rounded to fp16 as in the eager graph */
+int mc_geglu(const void* in, void* out, int64_t T, int I, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@
 // The frame pitch in shared memory is padded to 16 (mod 128) bytes so the 8 row addresses of every ldmatrix phase
 // fall in 8 different 16 B bank groups (rows of one (position, head) item are `pitch` apart).
 #include <math.h>
+#include <stdlib.h>
 
 #include "mc_common.cuh"
 
@@ -38,9 +39,14 @@ struct TACfg {
 };
 
 struct TileGeom {
-  int P, HG, W;        // positions / heads per tile, W = HG*DH halfs per (frame, position) row
-  int pitch;           // bytes between frames in one staged tensor
-  int tensor_bytes;    // bytes of one staged tensor (multiple of 128)
+  int P, HG, W;        // positions / heads per tile, W = HG*DH halfs per (frame, position) row of ONE tensor
+  int PS;              // halfs between positions inside a staged row: W, or 3W when Q|K|V are staged as one run
+  int fused;           // 1: q, k, v are column slices of one [.., 3C] buffer and the tile holds all heads ->
+                       //    ONE bulk copy per frame brings P positions x (Q|K|V) (P*3C*2 bytes)
+  int pitch;           // bytes between frames in the Q/K/V tile(s)
+  int pitch_x;         // bytes between frames in the extra tile of the backward (dO): rows of P*W halfs
+  int tensor_bytes;    // bytes of one staged Q/K/V tensor (separate mode) or of the fused tile
+  int x_bytes;         // bytes of the extra tile
 };
 
 struct TAParams {
@@ -66,39 +72,53 @@ struct TAParams {
 // values).
 template <int L>
 __device__ __forceinline__ uint32_t vrow_off(int idx, int pl0, const TileGeom& g) {
-  if (L == 8) return (idx & 7) * g.pitch + (min(pl0 + (idx >> 3), g.P - 1) * g.W) * 2;  // odd tail: pair with itself
-  return idx * g.pitch + (pl0 * g.W) * 2;
+  if (L == 8) return (idx & 7) * g.pitch + (min(pl0 + (idx >> 3), g.P - 1) * g.PS) * 2;  // odd tail: pair with itself
+  return idx * g.pitch + (pl0 * g.PS) * 2;
+}
+// same for the extra (dO / dQ) tile of the backward, whose rows are always P*W halfs
+template <int L>
+__device__ __forceinline__ uint32_t xrow_off(int idx, int pl0, const TileGeom& g) {
+  if (L == 8) return (idx & 7) * g.pitch_x + (min(pl0 + (idx >> 3), g.P - 1) * g.W) * 2;
+  return idx * g.pitch_x + (pl0 * g.W) * 2;
 }
 
 // Stage `ntensors` tensors (same layout) of this CTA's tile: rows of W halfs per (frame, position).
+// rows of `w` halfs per (frame, position); smem: frame pitch `spitch` bytes, position stride `sps` halfs.
+// When positions are contiguous on both sides (global stride_p == w == sps) one copy per frame moves all P of them.
 template <int L>
-__device__ __forceinline__ void stage_rows(uint8_t* sdst, const __half* gsrc, const mc_temporal_layout& lay,
-                                           int64_t gbase, const TileGeom& g, uint64_t* bar, int lane) {
-  const bool merged = (lay.stride_p == g.W);
-  const int ncopies = merged ? L : L * g.P;
-  const uint32_t bytes = (merged ? g.P : 1) * g.W * 2;
+__device__ __forceinline__ void stage_rows(uint8_t* sdst, int spitch, int sps, int w, int P, const __half* gsrc,
+                                           const mc_temporal_layout& lay, int64_t gbase, uint64_t* bar, int lane) {
+  const bool merged = (lay.stride_p == w) && (sps == w);
+  const int ncopies = merged ? L : L * P;
+  const uint32_t bytes = (merged ? P : 1) * w * 2;
   for (int i = lane; i < ncopies; i += 32) {
-    const int f = merged ? i : i / g.P;
-    const int pl = merged ? 0 : i % g.P;
-    bulk_g2s(sdst + f * g.pitch + pl * g.W * 2, gsrc + gbase + f * lay.stride_f + pl * lay.stride_p, bytes, bar);
+    const int f = merged ? i : i / P;
+    const int pl = merged ? 0 : i % P;
+    bulk_g2s(sdst + f * spitch + pl * sps * 2, gsrc + gbase + f * lay.stride_f + pl * lay.stride_p, bytes, bar);
   }
 }
 
 template <int L>
-__device__ __forceinline__ void store_rows(__half* gdst, const uint8_t* ssrc, const mc_temporal_layout& lay,
-                                           int64_t gbase, const TileGeom& g, int lane) {
-  const bool merged = (lay.stride_p == g.W);
-  const int ncopies = merged ? L : L * g.P;
-  const uint32_t bytes = (merged ? g.P : 1) * g.W * 2;
+__device__ __forceinline__ void store_rows(__half* gdst, const uint8_t* ssrc, int spitch, int sps, int w, int P,
+                                           const mc_temporal_layout& lay, int64_t gbase, int lane) {
+  const bool merged = (lay.stride_p == w) && (sps == w);
+  const int ncopies = merged ? L : L * P;
+  const uint32_t bytes = (merged ? P : 1) * w * 2;
   for (int i = lane; i < ncopies; i += 32) {
-    const int f = merged ? i : i / g.P;
-    const int pl = merged ? 0 : i % g.P;
-    bulk_s2g(gdst + gbase + f * lay.stride_f + pl * lay.stride_p, ssrc + f * g.pitch + pl * g.W * 2, bytes);
+    const int f = merged ? i : i / P;
+    const int pl = merged ? 0 : i % P;
+    bulk_s2g(gdst + gbase + f * lay.stride_f + pl * lay.stride_p, ssrc + f * spitch + pl * sps * 2, bytes);
   }
 }
 
 // S[mt] = Q K^T for one 16-row query tile: s[nt][0..3] in the m16n8 accumulator layout.
-template <typename C>
+template <int L, bool X>
+__device__ __forceinline__ uint32_t row_off(int idx, int pl0, const TileGeom& g) {
+  return X ? xrow_off<L>(idx, pl0, g) : vrow_off<L>(idx, pl0, g);
+}
+
+// AX / BX: operand lives in the extra (dO) tile rather than in the Q/K/V tile(s)
+template <typename C, bool AX = false, bool BX = false>
 __device__ __forceinline__ void qk_scores(float (&s)[C::NKT][4], uint32_t sQ, uint32_t sK, int mt, int pl0,
                                           int colbase, const TileGeom& g, int lane) {
 #pragma unroll
@@ -106,7 +126,7 @@ __device__ __forceinline__ void qk_scores(float (&s)[C::NKT][4], uint32_t sQ, ui
 #pragma unroll
     for (int e = 0; e < 4; ++e) s[nt][e] = 0.f;
   const int m = lane >> 3, r8 = lane & 7;
-  const uint32_t a_row = sQ + vrow_off<C::L>(mt * 16 + r8 + (m & 1) * 8, pl0, g) + (colbase + (m >> 1) * 8) * 2;
+  const uint32_t a_row = sQ + row_off<C::L, AX>(mt * 16 + r8 + (m & 1) * 8, pl0, g) + (colbase + (m >> 1) * 8) * 2;
 #pragma unroll
   for (int ks = 0; ks < C::KS; ++ks) {
     uint32_t a0, a1, a2, a3;
@@ -115,7 +135,7 @@ __device__ __forceinline__ void qk_scores(float (&s)[C::NKT][4], uint32_t sQ, ui
     for (int nt = 0; nt < C::NKT; nt += 2) {
       uint32_t b0, b1, b2, b3;
       const uint32_t b_row =
-          sK + vrow_off<C::L>((nt + (m >> 1)) * 8 + r8, pl0, g) + (colbase + ks * 16 + (m & 1) * 8) * 2;
+          sK + row_off<C::L, BX>((nt + (m >> 1)) * 8 + r8, pl0, g) + (colbase + ks * 16 + (m & 1) * 8) * 2;
       ldsm_x4(b0, b1, b2, b3, b_row);
       mma_16816(s[nt], a0, a1, a2, a3, b0, b1);
       mma_16816(s[nt + 1], a0, a1, a2, a3, b2, b3);
@@ -124,11 +144,11 @@ __device__ __forceinline__ void qk_scores(float (&s)[C::NKT][4], uint32_t sQ, ui
   if (C::KTAIL) {
     const int m2 = (lane >> 3) & 1;
     uint32_t a0, a1;
-    ldsm_x2(a0, a1, sQ + vrow_off<C::L>(mt * 16 + r8 + m2 * 8, pl0, g) + (colbase + C::DH - 8) * 2);
+    ldsm_x2(a0, a1, sQ + row_off<C::L, AX>(mt * 16 + r8 + m2 * 8, pl0, g) + (colbase + C::DH - 8) * 2);
 #pragma unroll
     for (int nt = 0; nt < C::NKT; nt += 2) {
       uint32_t b0, b1;
-      ldsm_x2(b0, b1, sK + vrow_off<C::L>((nt + m2) * 8 + r8, pl0, g) + (colbase + C::DH - 8) * 2);
+      ldsm_x2(b0, b1, sK + row_off<C::L, BX>((nt + m2) * 8 + r8, pl0, g) + (colbase + C::DH - 8) * 2);
       mma_1688(s[nt], a0, a1, b0);
       mma_1688(s[nt + 1], a0, a1, b1);
     }
@@ -182,7 +202,7 @@ __device__ __forceinline__ void softmax_rows(float (&s)[C::NKT][4], float scale)
 }
 
 // acc[nd][.] += A(16 x keys, register fragments pa[kk][0..3]) * T(keys x DH) with T row-major in smem (V, K, Q, dO)
-template <typename C>
+template <typename C, bool TX = false>
 __device__ __forceinline__ void mma_a_rowmajor_b(float (&acc)[C::NDT][4], const uint32_t (&pa)[C::KK][4],
                                                  uint32_t sT, int pl0, int colbase, const TileGeom& g, int lane) {
   const int m = lane >> 3, r8 = lane & 7;
@@ -192,27 +212,27 @@ __device__ __forceinline__ void mma_a_rowmajor_b(float (&acc)[C::NDT][4], const 
     for (int n0 = 0; n0 + 1 < C::NDT; n0 += 2) {
       uint32_t b0, b1, b2, b3;
       ldsm_x4_t(b0, b1, b2, b3,
-                sT + vrow_off<C::L>(kk * 16 + (m & 1) * 8 + r8, pl0, g) + (colbase + (n0 + (m >> 1)) * 8) * 2);
+                sT + row_off<C::L, TX>(kk * 16 + (m & 1) * 8 + r8, pl0, g) + (colbase + (n0 + (m >> 1)) * 8) * 2);
       mma_16816(acc[n0], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b0, b1);
       mma_16816(acc[n0 + 1], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b2, b3);
     }
     if (C::NDT & 1) {
       uint32_t b0, b1;
       ldsm_x2_t(b0, b1,
-                sT + vrow_off<C::L>(kk * 16 + ((lane >> 3) & 1) * 8 + r8, pl0, g) + (colbase + (C::NDT - 1) * 8) * 2);
+                sT + row_off<C::L, TX>(kk * 16 + ((lane >> 3) & 1) * 8 + r8, pl0, g) + (colbase + (C::NDT - 1) * 8) * 2);
       mma_16816(acc[C::NDT - 1], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b0, b1);
     }
   }
 }
 
 // write a 16 x DH fp32 accumulator tile (query/key tile mt) as fp16 into a staged tensor, scaled by `mul`
-template <typename C>
+template <typename C, bool TX = false>
 __device__ __forceinline__ void store_acc(const float (&acc)[C::NDT][4], float mul, uint8_t* sT_generic, int mt,
                                           int pl0, int colbase, const TileGeom& g, int lane) {
   const int gq = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf) {
-    uint8_t* row = sT_generic + vrow_off<C::L>(mt * 16 + gq + 8 * hf, pl0, g) + (colbase + 2 * t) * 2;
+    uint8_t* row = sT_generic + row_off<C::L, TX>(mt * 16 + gq + 8 * hf, pl0, g) + (colbase + 2 * t) * 2;
 #pragma unroll
     for (int nd = 0; nd < C::NDT; ++nd)
       *reinterpret_cast<__half2*>(row + nd * 16) = __floats2half2_rn(acc[nd][2 * hf] * mul, acc[nd][2 * hf + 1] * mul);
@@ -250,8 +270,8 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_fwd_kernel(const TAPara
   uint64_t* bar_v = bar_qk + 1;
   const TileGeom g = prm.g;
   uint8_t* sQ = smem + kHeaderBytes;
-  uint8_t* sK = sQ + g.tensor_bytes;
-  uint8_t* sV = sK + g.tensor_bytes;
+  uint8_t* sK = g.fused ? sQ + g.W * 2 : sQ + g.tensor_bytes;       // fused: K, V are column offsets of one tile
+  uint8_t* sV = g.fused ? sQ + g.W * 4 : sQ + 2 * g.tensor_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_hg = prm.H / g.HG, n_pt = prm.D / g.P;
@@ -271,15 +291,21 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_fwd_kernel(const TAPara
   __syncthreads();
   if (warp == 0) {
     const uint32_t tbytes = (uint32_t)L * g.P * g.W * 2;
-    if (lane == 0) {
-      mbar_arrive_expect_tx(bar_qk, 2 * tbytes);
-      if (has_o) mbar_arrive_expect_tx(bar_v, tbytes);
-    }
-    __syncwarp();
     const int64_t gbase = (int64_t)b * prm.in.stride_b + (int64_t)p0 * prm.in.stride_p + h0 * DH;
-    stage_rows<L>(sQ, prm.q, prm.in, gbase, g, bar_qk, lane);
-    stage_rows<L>(sK, prm.k, prm.in, gbase, g, bar_qk, lane);
-    if (has_o) stage_rows<L>(sV, prm.v, prm.in, gbase, g, bar_v, lane);
+    if (g.fused) {
+      if (lane == 0) mbar_arrive_expect_tx(bar_qk, 3 * tbytes);
+      __syncwarp();
+      stage_rows<L>(sQ, g.pitch, g.PS, 3 * g.W, g.P, prm.q, prm.in, gbase, bar_qk, lane);
+    } else {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar_qk, 2 * tbytes);
+        if (has_o) mbar_arrive_expect_tx(bar_v, tbytes);
+      }
+      __syncwarp();
+      stage_rows<L>(sQ, g.pitch, g.PS, g.W, g.P, prm.q, prm.in, gbase, bar_qk, lane);
+      stage_rows<L>(sK, g.pitch, g.PS, g.W, g.P, prm.k, prm.in, gbase, bar_qk, lane);
+      if (has_o) stage_rows<L>(sV, g.pitch, g.PS, g.W, g.P, prm.v, prm.in, gbase, bar_v, lane);
+    }
   }
   mbar_wait(bar_qk, 0);
 
@@ -359,7 +385,7 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_fwd_kernel(const TAPara
       // ---- O = P V, written over this item's Q rows ----
       if (has_o) {
         if (!v_ready) {
-          mbar_wait(bar_v, 0);
+          if (!g.fused) mbar_wait(bar_v, 0);
           v_ready = true;
         }
         uint32_t pa[C::KK][4];
@@ -381,7 +407,7 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_fwd_kernel(const TAPara
     __syncthreads();
     if (warp == 0) {
       const int64_t obase = (int64_t)b * prm.out.stride_b + (int64_t)p0 * prm.out.stride_p + h0 * DH;
-      store_rows<L>(prm.o, sQ, prm.out, obase, g, lane);
+      store_rows<L>(prm.o, sQ, g.pitch, g.PS, g.W, g.P, prm.out, obase, lane);
       bulk_commit();
       bulk_wait_read_all();
     }
@@ -401,9 +427,12 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_bwd_kernel(const TAPara
   uint64_t* bar_v = bar_qk + 1;
   const TileGeom g = prm.g;
   uint8_t* sQ = smem + kHeaderBytes;
-  uint8_t* sK = sQ + g.tensor_bytes;
-  uint8_t* sV = sK + g.tensor_bytes;
-  uint8_t* sD = sV + g.tensor_bytes;  // dO, later dQ
+  uint8_t* sK = g.fused ? sQ + g.W * 2 : sQ + g.tensor_bytes;
+  uint8_t* sV = g.fused ? sQ + g.W * 4 : sQ + 2 * g.tensor_bytes;
+  uint8_t* sD = sQ + (g.fused ? 1 : 3) * g.tensor_bytes;  // extra tile: dO, later dQ
+  // outputs as one [.., 3C] buffer too: dQ is moved next to dK, dV and each frame leaves with ONE bulk store
+  const bool fused_out = g.fused && prm.out.stride_p == 3 * g.W && prm.dk == prm.dq + g.W &&
+                         (prm.dv == nullptr || prm.dv == prm.dq + 2 * g.W);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_hg = prm.H / g.HG, n_pt = prm.D / g.P;
@@ -423,18 +452,28 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_bwd_kernel(const TAPara
   __syncthreads();
   if (warp == 0) {
     const uint32_t tbytes = (uint32_t)L * g.P * g.W * 2;
-    if (lane == 0) {
-      mbar_arrive_expect_tx(bar_qk, 2 * tbytes);
-      if (has_do) mbar_arrive_expect_tx(bar_v, 2 * tbytes);
-    }
-    __syncwarp();
     const int64_t gbase = (int64_t)b * prm.in.stride_b + (int64_t)p0 * prm.in.stride_p + h0 * DH;
-    stage_rows<L>(sQ, prm.q, prm.in, gbase, g, bar_qk, lane);
-    stage_rows<L>(sK, prm.k, prm.in, gbase, g, bar_qk, lane);
-    if (has_do) {
-      const int64_t dbase = (int64_t)b * prm.dol.stride_b + (int64_t)p0 * prm.dol.stride_p + h0 * DH;
-      stage_rows<L>(sV, prm.v, prm.in, gbase, g, bar_v, lane);
-      stage_rows<L>(sD, prm.d_o, prm.dol, dbase, g, bar_v, lane);
+    const int64_t dbase = (int64_t)b * prm.dol.stride_b + (int64_t)p0 * prm.dol.stride_p + h0 * DH;
+    if (g.fused) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar_qk, 3 * tbytes);
+        if (has_do) mbar_arrive_expect_tx(bar_v, tbytes);
+      }
+      __syncwarp();
+      stage_rows<L>(sQ, g.pitch, g.PS, 3 * g.W, g.P, prm.q, prm.in, gbase, bar_qk, lane);
+      if (has_do) stage_rows<L>(sD, g.pitch_x, g.W, g.W, g.P, prm.d_o, prm.dol, dbase, bar_v, lane);
+    } else {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar_qk, 2 * tbytes);
+        if (has_do) mbar_arrive_expect_tx(bar_v, 2 * tbytes);
+      }
+      __syncwarp();
+      stage_rows<L>(sQ, g.pitch, g.PS, g.W, g.P, prm.q, prm.in, gbase, bar_qk, lane);
+      stage_rows<L>(sK, g.pitch, g.PS, g.W, g.P, prm.k, prm.in, gbase, bar_qk, lane);
+      if (has_do) {
+        stage_rows<L>(sV, g.pitch, g.PS, g.W, g.P, prm.v, prm.in, gbase, bar_v, lane);
+        stage_rows<L>(sD, g.pitch_x, g.W, g.W, g.P, prm.d_o, prm.dol, dbase, bar_v, lane);
+      }
     }
   }
   mbar_wait(bar_qk, 0);
@@ -463,7 +502,7 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_bwd_kernel(const TAPara
       // dP = dO V^T  (+ dense d_probs, + one-hot d_gathered)
       float dp[C::NKT][4];
       if (has_do) {
-        qk_scores<C>(dp, sDa, sVa, mt, pl0, colbase, g, lane);
+        qk_scores<C, true, false>(dp, sDa, sVa, mt, pl0, colbase, g, lane);
 #pragma unroll
         for (int nt = 0; nt < C::NKT; ++nt)
 #pragma unroll
@@ -530,7 +569,7 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_bwd_kernel(const TAPara
           at[mt][2] = movmatrix_t(pfrag[mt][kt][1]);
           at[mt][3] = movmatrix_t(pfrag[mt][kt][3]);
         }
-        mma_a_rowmajor_b<C>(acc, at, sDa, pl0, colbase, g, lane);
+        mma_a_rowmajor_b<C, true>(acc, at, sDa, pl0, colbase, g, lane);
         // dV tile kt goes over V rows [kt*16, +16); V is still needed by nobody (dP done for all tiles above)
         store_acc<C>(acc, 1.f, sV, kt, pl0, colbase, g, lane);
       }
@@ -546,7 +585,7 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_bwd_kernel(const TAPara
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
       mma_a_rowmajor_b<C>(acc, dsfrag[mt], sKa, pl0, colbase, g, lane);
-      store_acc<C>(acc, prm.scale, sD, mt, pl0, colbase, g, lane);
+      store_acc<C, true>(acc, prm.scale, sD, mt, pl0, colbase, g, lane);
     }
     __syncwarp();
 
@@ -569,15 +608,31 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_bwd_kernel(const TAPara
       mma_a_rowmajor_b<C>(acc, at, sQa, pl0, colbase, g, lane);
       store_acc<C>(acc, prm.scale, sK, kt, pl0, colbase, g, lane);
     }
+    if (fused_out) {  // Q is dead now: move this item's dQ rows (extra tile) over its Q columns, 16 B per lane-step
+      __syncwarp();
+      constexpr int kChunks = DH / 8;
+      constexpr int kRows = (L == 8) ? 16 : L;
+      for (int i = lane; i < kRows * kChunks; i += 32) {
+        const int r = i / kChunks, ch = i % kChunks;
+        const uint4 val = *reinterpret_cast<const uint4*>(sD + xrow_off<L>(r, pl0, g) + (colbase + ch * 8) * 2);
+        *reinterpret_cast<uint4*>(sQ + vrow_off<L>(r, pl0, g) + (colbase + ch * 8) * 2) = val;
+      }
+    }
   }
 
   fence_proxy_async();
   __syncthreads();
   if (warp == 0) {
     const int64_t obase = (int64_t)b * prm.out.stride_b + (int64_t)p0 * prm.out.stride_p + h0 * DH;
-    store_rows<L>(prm.dq, sD, prm.out, obase, g, lane);
-    store_rows<L>(prm.dk, sK, prm.out, obase, g, lane);
-    if (has_do && prm.dv != nullptr) store_rows<L>(prm.dv, sV, prm.out, obase, g, lane);
+    if (fused_out && (prm.dv != nullptr && has_do)) {
+      store_rows<L>(prm.dq, sQ, g.pitch, g.PS, 3 * g.W, g.P, prm.out, obase, lane);  // dQ | dK | dV per frame
+    } else if (fused_out) {  // no dV: two column blocks per (frame, position)
+      store_rows<L>(prm.dq, sQ, g.pitch, g.PS, 2 * g.W, g.P, prm.out, obase, lane);
+    } else {
+      store_rows<L>(prm.dq, sD, g.pitch_x, g.W, g.W, g.P, prm.out, obase, lane);
+      store_rows<L>(prm.dk, sK, g.pitch, g.PS, g.W, g.P, prm.out, obase, lane);
+      if (has_do && prm.dv != nullptr) store_rows<L>(prm.dv, sV, g.pitch, g.PS, g.W, g.P, prm.out, obase, lane);
+    }
     bulk_commit();
     bulk_wait_read_all();
   }
@@ -586,25 +641,47 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_bwd_kernel(const TAPara
 // ================================================================================================================
 // host side
 // ================================================================================================================
-static bool choose_geom(int D, int L, int H, int DH, int ntensors, bool need_even_p, TileGeom* g) {
-  // tile bytes target: several CTAs per SM so one CTA's loads overlap another's math (227 KB smem / SM)
-  const int target = (ntensors == 3) ? 64 * 1024 : 84 * 1024;
-  int HG = H;
+static int pad16(int row_bytes) { return row_bytes + ((16 - (row_bytes % 128)) + 128) % 128; }
+
+// ntensors: 3 (fwd: Q,K,V) or 4 (bwd: + dO). `fusable`: q, k, v are the three column blocks of one [.., 3C] buffer.
+static bool choose_geom(int D, int L, int H, int DH, int ntensors, bool need_even_p, bool fusable, TileGeom* g) {
+  // Tile size: ~32 KB per Q/K/V set keeps 6-7 CTAs resident per SM (227 KB), which is what de-synchronises their
+  // load / math / store phases (measured on B200: 61 KB tiles reach 54 % of the HBM roof at C=320, 30 KB tiles 62-75 %).
+  // Tiles that would hold fewer than 4 (position, head) items get twice the budget instead of idle warps.
+  static const int env_kb = getenv("MC_TILE_KB") ? atoi(getenv("MC_TILE_KB")) : 0;  // tuning knob (KB per Q/K/V set)
+  const int base = (env_kb > 0 ? env_kb : 32) * 1024 * ntensors / 3;
   auto tbytes = [&](int P, int hg) { return (int64_t)ntensors * L * P * hg * DH * 2; };
   const int Pmin = (need_even_p && D % 2 == 0) ? 2 : 1;  // L == 8 packs two positions per item; odd D: tail pairs with itself
-  while (HG > 1 && tbytes(Pmin, HG) > target && (HG % 2 == 0)) HG /= 2;
-  int P = Pmin;
-  if (HG == H) {  // whole positions are contiguous runs: grow P while the tile stays small and there is enough work
-    while (D % (P * 2) == 0 && tbytes(P * 2, HG) <= target && P < 8) P *= 2;
+  const int pp = need_even_p ? 2 : 1;
+  int HG = H, P = Pmin, target = base;
+  for (int attempt = 0; attempt < 2; ++attempt, target *= 2) {
+    HG = H;
+    while (HG > 1 && tbytes(Pmin, HG) > target && (HG % 2 == 0)) HG /= 2;
+    P = Pmin;
+    if (HG == H) {  // whole positions are contiguous runs: grow P while the tile stays within budget
+      while (D % (P * 2) == 0 && tbytes(P * 2, HG) <= target && P < 8) P *= 2;
+    }
+    if (((P + pp - 1) / pp) * HG >= 4) break;
   }
   g->P = P;
   g->HG = HG;
   g->W = HG * DH;
-  const int row = P * g->W * 2;
-  const int pad = ((16 - (row % 128)) + 128) % 128;
-  g->pitch = row + pad;
+  g->fused = (fusable && HG == H) ? 1 : 0;
+  g->PS = g->fused ? 3 * g->W : g->W;
+  g->pitch = pad16(P * g->PS * 2);
+  g->pitch_x = pad16(P * g->W * 2);
   g->tensor_bytes = ((L * g->pitch) + 127) / 128 * 128;
+  g->x_bytes = ((L * g->pitch_x) + 127) / 128 * 128;
   return true;
+}
+
+static int tile_smem(const TileGeom& g, int ntensors) {
+  const int qkv = g.fused ? g.tensor_bytes : 3 * g.tensor_bytes;
+  return kHeaderBytes + qkv + (ntensors == 4 ? g.x_bytes : 0);
+}
+
+static bool is_fusable(const TAParams& prm, int C) {
+  return prm.v != nullptr && prm.k == prm.q + C && prm.v == prm.q + 2 * C && prm.in.stride_p == 3 * C;
 }
 
 static bool layout_ok(const mc_temporal_layout& l) {
@@ -613,14 +690,12 @@ static bool layout_ok(const mc_temporal_layout& l) {
 
 template <int DH, int L>
 static int launch_fwd(TAParams& prm, cudaStream_t st) {
-  if (!choose_geom(prm.D, L, prm.H, DH, 3, L == 8, &prm.g)) {
-    set_error("temporal_attn_fwd: D=%d must be even for L=8", prm.D);
-    return MC_E_INVALID;
-  }
-  const int smem = kHeaderBytes + 3 * prm.g.tensor_bytes;
+  choose_geom(prm.D, L, prm.H, DH, 3, L == 8, is_fusable(prm, prm.H * DH) && prm.o != nullptr, &prm.g);
+  const int smem = tile_smem(prm.g, 3);
   const int64_t grid = (int64_t)prm.B * (prm.D / prm.g.P) * (prm.H / prm.g.HG);
   const int n_items = ((prm.g.P + TACfg<DH, L>::PP - 1) / TACfg<DH, L>::PP) * prm.g.HG;
-  if (n_items >= 8) {  // one (position, head) item per warp pass: more warps hide the ldmatrix -> mma -> shuffle latency
+  static const int env_nw = getenv("MC_WARPS") ? atoi(getenv("MC_WARPS")) : 0;  // tuning knob
+  if (env_nw ? env_nw == 8 : n_items >= 16) {
     auto kern = temporal_attn_fwd_kernel<DH, L, 8>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     kern<<<(unsigned)grid, 8 * 32, smem, st>>>(prm);
@@ -635,14 +710,11 @@ static int launch_fwd(TAParams& prm, cudaStream_t st) {
 
 template <int DH, int L>
 static int launch_bwd(TAParams& prm, cudaStream_t st) {
-  if (!choose_geom(prm.D, L, prm.H, DH, 4, L == 8, &prm.g)) {
-    set_error("temporal_attn_bwd: D=%d must be even for L=8", prm.D);
-    return MC_E_INVALID;
-  }
-  const int smem = kHeaderBytes + 4 * prm.g.tensor_bytes;
+  choose_geom(prm.D, L, prm.H, DH, 4, L == 8, is_fusable(prm, prm.H * DH), &prm.g);
+  const int smem = tile_smem(prm.g, 4);
   const int64_t grid = (int64_t)prm.B * (prm.D / prm.g.P) * (prm.H / prm.g.HG);
   const int n_items = ((prm.g.P + TACfg<DH, L>::PP - 1) / TACfg<DH, L>::PP) * prm.g.HG;
-  if (n_items >= 8) {
+  if (n_items >= 16) {
     auto kern = temporal_attn_bwd_kernel<DH, L, 8>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     kern<<<(unsigned)grid, 8 * 32, smem, st>>>(prm);

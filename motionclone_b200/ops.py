@@ -107,9 +107,17 @@ def temporal_attention_forward(q: Tensor, k: Tensor, v: Optional[Tensor], heads:
     return o, probs, ((tv, ti) if want_top1 else None), gathered
 
 
+def _is_fused_qkv(q: Tensor, k: Tensor, v: Optional[Tensor]) -> bool:
+    c = q.shape[-1]
+    return (v is not None and q.stride(2) == 3 * c and k.data_ptr() == q.data_ptr() + 2 * c
+            and v.data_ptr() == q.data_ptr() + 4 * c)
+
+
 def temporal_attention_backward(q: Tensor, k: Tensor, v: Optional[Tensor], heads: int, scale: float,
                                 d_o: Optional[Tensor], d_probs: Optional[Tensor], gather_idx: Optional[Tensor],
-                                d_gathered: Optional[Tensor], need_dv: bool = True):
+                                d_gathered: Optional[Tensor], need_dv: bool = True, return_fused: bool = False):
+    """-> (dq, dk, dv). When q, k, v are the column blocks of one fused [B, F, P, 3C] buffer the gradients are written
+    as the column blocks of one [B, F, P, 3C] buffer too (`return_fused=True` returns that buffer instead)."""
     B, F, P, C = q.shape
     lay = _layout_bfpc(q)
     if d_o is not None:
@@ -120,53 +128,71 @@ def temporal_attention_backward(q: Tensor, k: Tensor, v: Optional[Tensor], heads
         d_probs = d_probs.contiguous()
     if d_gathered is not None:
         d_gathered = d_gathered.contiguous()
-    dq = torch.empty((B, F, P, C), dtype=q.dtype, device=q.device)
-    dk = torch.empty_like(dq)
-    dv = torch.empty_like(dq) if (need_dv and d_o is not None) else None
+    want_dv = need_dv and d_o is not None
+    fused = _is_fused_qkv(q, k, v)
+    if fused:
+        dqkv = torch.empty((B, F, P, 3 * C), dtype=q.dtype, device=q.device)
+        dq, dk, dv = dqkv[..., :C], dqkv[..., C:2 * C], dqkv[..., 2 * C:]
+        if not want_dv:
+            dv.zero_()
+    else:
+        dqkv = None
+        dq = torch.empty((B, F, P, C), dtype=q.dtype, device=q.device)
+        dk = torch.empty_like(dq)
+        dv = torch.empty_like(dq) if want_dv else None
     ev0 = TIMER.start() if TIMER is not None else None
     st = _lib.lib().mc_temporal_attn_bwd(_ptr(q), _ptr(k), _ptr(v), lay,
                                          _ptr(d_o), _layout_bfpc(d_o) if d_o is not None else TemporalLayout(0, 0, 0),
                                          _ptr(d_probs), _ptr(gather_idx), _ptr(d_gathered),
-                                         _ptr(dq), _ptr(dk), _ptr(dv), _layout_bfpc(dq),
+                                         _ptr(dq), _ptr(dk), _ptr(dv if want_dv else None), _layout_bfpc(dq),
                                          B, P, F, heads, C // heads, float(scale), _stream())
     _lib.check(st, "mc_temporal_attn_bwd")
     if ev0 is not None:  # Q, K (V, dO) read; dQ, dK (dV) written
         TIMER.stop("temporal_attn_bwd", (7 if d_o is not None else 4) * B * F * P * C * 2, ev0)
-    return dq, dk, dv
+    if return_fused:
+        if not fused:
+            raise ValueError("return_fused needs q, k, v to be column blocks of one [.., 3C] buffer")
+        return dqkv
+    return dq, dk, (dv if (want_dv or fused) else None)
 
 
 class TemporalAttention(torch.autograd.Function):
-    """o, probs, gathered = f(q, k, v); any of the three outputs can be switched off.
+    """o, probs, gathered = f(qkv) with qkv = [B, F, P, 3C] (one fused projection; q | k | v column blocks); probs and
+    gathered can be switched off.
 
-    Backward recomputes the probabilities in-kernel and sums the three incoming gradient branches before the softmax
-    backward (the reference builds them as separate autograd branches off the same q, k:
-    models/attention.py:461-490 for o and :564-611 via utils/motionclone_functions.py:279 for the probabilities).
+    Backward recomputes the probabilities in-kernel, sums the three incoming gradient branches before the softmax
+    backward (the reference builds them as separate autograd branches off the same q, k: models/attention.py:461-490
+    for o and :564-611 via utils/motionclone_functions.py:279 for the probabilities) and writes ONE [B, F, P, 3C]
+    gradient, so autograd sees a single edge instead of three slice-backward zero-fills.
     """
 
     @staticmethod
-    def forward(ctx, q, k, v, heads: int, scale: float, want_probs: bool, gather_idx):
+    def forward(ctx, qkv, heads: int, scale: float, want_probs: bool, gather_idx):
+        c = qkv.shape[-1] // 3
+        q, k, v = qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
         o, probs, _, gathered = temporal_attention_forward(q, k, v, heads, scale, want_o=True, want_probs=want_probs,
                                                            gather_idx=gather_idx)
-        ctx.save_for_backward(q, k, v, gather_idx)
+        ctx.save_for_backward(qkv, gather_idx)
         ctx.heads, ctx.scale = heads, scale
-        outs = (o, probs if probs is not None else q.new_empty(0), gathered if gathered is not None else q.new_empty(0))
+        outs = (o, probs if probs is not None else qkv.new_empty(0),
+                gathered if gathered is not None else qkv.new_empty(0))
         ctx.mark_non_differentiable(*[t for t, used in ((outs[1], want_probs), (outs[2], gather_idx is not None))
                                       if not used])
         return outs
 
     @staticmethod
     def backward(ctx, d_o, d_probs, d_gathered):
-        q, k, v, gather_idx = ctx.saved_tensors
+        qkv, gather_idx = ctx.saved_tensors
+        c = qkv.shape[-1] // 3
+        q, k, v = qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
         if d_probs is not None and d_probs.numel() == 0:
             d_probs = None
         if d_gathered is not None and d_gathered.numel() == 0:
             d_gathered = None
-        dq, dk, dv = temporal_attention_backward(q, k, v, ctx.heads, ctx.scale, d_o, d_probs,
-                                                 gather_idx if d_gathered is not None else None, d_gathered,
-                                                 need_dv=ctx.needs_input_grad[2])
-        if dv is None and ctx.needs_input_grad[2]:
-            dv = torch.zeros_like(q)
-        return dq, dk, dv, None, None, None, None
+        dqkv = temporal_attention_backward(q, k, v, ctx.heads, ctx.scale, d_o, d_probs,
+                                           gather_idx if d_gathered is not None else None, d_gathered,
+                                           need_dv=True, return_fused=True)
+        return dqkv, None, None, None, None
 
 
 class TemporalProbs(torch.autograd.Function):
@@ -283,4 +309,55 @@ def add_noise(x0: Tensor, noise: Tensor, alpha_t: Tensor) -> Tensor:
     st = _lib.lib().mc_add_noise(_ptr(x0), _ptr(noise), _ptr(out), x0.numel(), float(a ** 0.5), float((1 - a) ** 0.5),
                                  _stream())
     _lib.check(st, "mc_add_noise")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# NHWC GroupNorm(+SiLU), LayerNorm, GEGLU (inference passes)
+# ----------------------------------------------------------------------------------------------------------------
+_gn_workspace = {}
+
+
+def fast_path_ok(x: Tensor) -> bool:
+    """The fused glue kernels serve the no-grad passes (uncond / plain steps, up-blocks beyond the guidance cut)."""
+    return x.is_cuda and x.dtype == torch.float16 and not torch.is_grad_enabled()
+
+
+def groupnorm_nhwc(x: Tensor, weight: Tensor, bias: Tensor, groups: int, eps: float, silu: bool = False) -> Tensor:
+    """x: [N, C, h, w] in channels_last (physically [N, h, w, C]); returns the same format."""
+    _require(x, "x")
+    if x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("groupnorm_nhwc expects a 4-D channels_last tensor")
+    N, C, H, W = x.shape
+    y = torch.empty_like(x)  # preserves channels_last
+    need = int(_lib.lib().mc_groupnorm_workspace_bytes(N, groups))
+    key = (x.device, torch.cuda.current_stream().cuda_stream)
+    ws = _gn_workspace.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=x.device)
+        _gn_workspace[key] = ws
+    st = _lib.lib().mc_groupnorm_nhwc(_ptr(x), _ptr(y), _ptr(weight), _ptr(bias), _ptr(ws), ws.numel(), N, H * W, C,
+                                      groups, float(eps), int(silu), _stream())
+    _lib.check(st, "mc_groupnorm_nhwc")
+    return y
+
+
+def layernorm(x: Tensor, weight: Tensor, bias: Tensor, eps: float) -> Tensor:
+    _require(x, "x")
+    x = x.contiguous()
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    st = _lib.lib().mc_layernorm(_ptr(x), _ptr(y), _ptr(weight), _ptr(bias), x.numel() // C, C, float(eps), _stream())
+    _lib.check(st, "mc_layernorm")
+    return y
+
+
+def geglu(x: Tensor) -> Tensor:
+    """x [..., 2I] = [h | gate] -> h * gelu_erf(gate) [..., I]."""
+    _require(x, "x")
+    x = x.contiguous()
+    I = x.shape[-1] // 2
+    out = torch.empty(x.shape[:-1] + (I,), dtype=x.dtype, device=x.device)
+    st = _lib.lib().mc_geglu(_ptr(x), _ptr(out), x.numel() // (2 * I), I, _stream())
+    _lib.check(st, "mc_geglu")
     return out

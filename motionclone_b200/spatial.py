@@ -22,6 +22,30 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import ops
+
+
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm (same parameters / state-dict keys); inference passes run csrc/norm_act.cu's warp-per-row kernel."""
+
+    def forward(self, x):
+        if ops.fast_path_ok(x) and self.elementwise_affine and x.shape[-1] % 8 == 0 and x.shape[-1] <= 2048:
+            return ops.layernorm(x, self.weight, self.bias, self.eps)
+        return super().forward(x)
+
+
+class GroupNormNHWC(nn.GroupNorm):
+    """nn.GroupNorm (same parameters / state-dict keys) that reads channels_last activations directly in inference
+    passes, optionally fusing the SiLU that follows it in the resnet blocks. ATen's CUDA GroupNorm converts a
+    channels_last input to NCHW first (a copy) and hands NCHW to the next cuDNN conv (another copy)."""
+
+    def forward(self, x, silu: bool = False):
+        if x.dim() == 4 and ops.fast_path_ok(x) and x.shape[1] % 8 == 0 and x.shape[1] <= 4096 \
+                and x.is_contiguous(memory_format=torch.channels_last):
+            return ops.groupnorm_nhwc(x, self.weight, self.bias, self.num_groups, self.eps, silu)
+        y = super().forward(x)
+        return F.silu(y) if silu else y
+
 
 class GEGLU(nn.Module):
     """diffusers 0.16 GEGLU: Linear(d, 2*inner) -> h * gelu_erf(gate)."""
@@ -31,7 +55,10 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
-        h, gate = self.proj(x).chunk(2, dim=-1)
+        y = self.proj(x)
+        if ops.fast_path_ok(y):
+            return ops.geglu(y)  # one pass instead of chunk -> gelu -> mul (csrc/norm_act.cu)
+        h, gate = y.chunk(2, dim=-1)
         return h * F.gelu(gate)
 
 
@@ -181,16 +208,16 @@ class BasicTransformerBlock(nn.Module):
         self.unet_use_temporal_attention = unet_use_temporal_attention
         self.attn1 = CrossAttention(query_dim=dim, heads=num_attention_heads, dim_head=attention_head_dim,
                                     dropout=dropout, bias=attention_bias, upcast_attention=upcast_attention)
-        self.norm1 = nn.LayerNorm(dim)
+        self.norm1 = LayerNorm(dim)
         if cross_attention_dim is not None:
             self.attn2 = CrossAttention(query_dim=dim, cross_attention_dim=cross_attention_dim,
                                         heads=num_attention_heads, dim_head=attention_head_dim, dropout=dropout,
                                         bias=attention_bias, upcast_attention=upcast_attention)
-            self.norm2 = nn.LayerNorm(dim)
+            self.norm2 = LayerNorm(dim)
         else:
             self.attn2 = self.norm2 = None
         self.ff = FeedForward(dim, dropout=dropout, activation_fn=activation_fn)
-        self.norm3 = nn.LayerNorm(dim)
+        self.norm3 = LayerNorm(dim)
 
     def set_use_memory_efficient_attention_xformers(self, use: bool, op=None):
         self.attn1._use_memory_efficient_attention_xformers = use
@@ -225,7 +252,7 @@ class Transformer3DModel(nn.Module):
         self.attention_head_dim = attention_head_dim
         inner_dim = num_attention_heads * attention_head_dim
         self.in_channels = in_channels
-        self.norm = nn.GroupNorm(num_groups=norm_num_groups, num_channels=in_channels, eps=1e-6, affine=True)
+        self.norm = GroupNormNHWC(num_groups=norm_num_groups, num_channels=in_channels, eps=1e-6, affine=True)
         if use_linear_projection:
             self.proj_in = nn.Linear(in_channels, inner_dim)
             self.proj_out = nn.Linear(in_channels, inner_dim)

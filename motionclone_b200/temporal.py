@@ -22,7 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .spatial import CrossAttention, FeedForward
+from .spatial import CrossAttention, FeedForward, GroupNormNHWC, LayerNorm
 
 
 def zero_module(module: nn.Module) -> nn.Module:
@@ -135,8 +135,7 @@ class VersatileAttention(CrossAttention):
             mode = proc.mode
         gather_idx = proc.ref_idx if mode == "gather" else None
         if torch.is_grad_enabled() and qkv.requires_grad:
-            o, probs, gathered = ops.TemporalAttention.apply(q, k, v, self.heads, self.scale, mode == "probs",
-                                                             gather_idx)
+            o, probs, gathered = ops.TemporalAttention.apply(qkv, self.heads, self.scale, mode == "probs", gather_idx)
             top1 = None
             if mode == "top1":
                 top1 = ops.top1_rows(ops.TemporalProbs.apply(q, k, self.heads, self.scale).detach())
@@ -171,11 +170,11 @@ class TemporalTransformerBlock(nn.Module):
                 cross_frame_attention_mode=cross_frame_attention_mode,
                 temporal_position_encoding=temporal_position_encoding,
                 temporal_position_encoding_max_len=temporal_position_encoding_max_len))
-            norms.append(nn.LayerNorm(dim))
+            norms.append(LayerNorm(dim))
         self.attention_blocks = nn.ModuleList(blocks)
         self.norms = nn.ModuleList(norms)
         self.ff = FeedForward(dim, dropout=dropout, activation_fn=activation_fn)
-        self.ff_norm = nn.LayerNorm(dim)
+        self.ff_norm = LayerNorm(dim)
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, video_length=None):
         for attn, norm in zip(self.attention_blocks, self.norms):
@@ -196,7 +195,7 @@ class TemporalTransformer3DModel(nn.Module):
                  temporal_position_encoding_max_len=24):
         super().__init__()
         inner_dim = num_attention_heads * attention_head_dim
-        self.norm = nn.GroupNorm(num_groups=norm_num_groups, num_channels=in_channels, eps=1e-6, affine=True)
+        self.norm = GroupNormNHWC(num_groups=norm_num_groups, num_channels=in_channels, eps=1e-6, affine=True)
         self.proj_in = nn.Linear(in_channels, inner_dim)
         self.transformer_blocks = nn.ModuleList([
             TemporalTransformerBlock(dim=inner_dim, num_attention_heads=num_attention_heads,

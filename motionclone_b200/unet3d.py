@@ -23,7 +23,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .spatial import Transformer3DModel
+from .spatial import GroupNormNHWC, Transformer3DModel
 from .temporal import get_motion_module
 
 CL = torch.channels_last
@@ -52,14 +52,14 @@ class InflatedConv3d(nn.Conv2d):
         return _unfold5(super().forward(x4), bf)
 
 
-class InflatedGroupNorm(nn.GroupNorm):
-    """resnet.py:21-29."""
+class InflatedGroupNorm(GroupNormNHWC):
+    """resnet.py:21-29; 4-D channels_last inputs take the NHWC kernel (optionally with the SiLU that follows)."""
 
-    def forward(self, x):
+    def forward(self, x, silu: bool = False):
         if x.dim() == 4:
-            return super().forward(x)
+            return super().forward(x, silu)
         x4, bf = _fold5(x)
-        return _unfold5(super().forward(x4), bf)
+        return _unfold5(super().forward(x4, silu), bf)
 
 
 class Upsample3D(nn.Module):
@@ -129,11 +129,11 @@ class ResnetBlock3D(nn.Module):
     def forward(self, x, temb_act):
         """x `[(b f), C, h, w]`; temb_act `[b, temb_channels]` = SiLU(time embedding) (resnet.py:192 applies the SiLU
         in every block; it is hoisted). The projection runs once per batch element and is broadcast over frames."""
-        h = self.conv1(F.silu(self.norm1(x)))
+        h = self.conv1(self.norm1(x, silu=True))
         if self.time_emb_proj is not None:
             t = self.time_emb_proj(temb_act)
             h = h + t.repeat_interleave(x.shape[0] // t.shape[0], dim=0)[:, :, None, None]
-        h = self.conv2(self.dropout(F.silu(self.norm2(h))))
+        h = self.conv2(self.dropout(self.norm2(h, silu=True)))
         if self.keep_hidden_state:
             self.record_hidden_state = h
         if self.conv_shortcut is not None:
@@ -557,6 +557,6 @@ class UNet3DConditionModel(nn.Module):
                 with torch.no_grad():  # :629
                     x = blk(x, res, temb, encoder_hidden_states, f, upsample_size=size)
 
-        x = self.conv_out(self.conv_act(self.conv_norm_out(x)))
+        x = self.conv_out(self.conv_norm_out(x, silu=True))  # conv_act (SiLU) fused into the norm
         out = x.reshape(b, f, x.shape[1], hh, ww).permute(0, 2, 1, 3, 4)
         return UNet3DConditionOutput(sample=out) if return_dict else (out,)

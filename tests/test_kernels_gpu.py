@@ -195,7 +195,8 @@ def _close(a, b, rel=2e-2, name=""):
 @pytest.mark.parametrize("L,H,DH,B,P", [(16, 8, 40, 1, 16), (16, 8, 160, 1, 4), (16, 8, 80, 2, 8), (8, 8, 40, 1, 8),
                                         (8, 8, 16, 1, 4), (8, 8, 40, 1, 1), (8, 8, 16, 1, 3), (32, 8, 40, 1, 4), (32, 8, 160, 1, 2), (16, 8, 8, 1, 4)])
 @pytest.mark.parametrize("branches", ["o", "o+gather", "gather", "probs", "all"])
-def test_temporal_attention_backward(L, H, DH, B, P, branches):
+@pytest.mark.parametrize("fused", [True, False])
+def test_temporal_attention_backward(L, H, DH, B, P, branches, fused):
     ops, dev = _ops(), _dev()
     C = H * DH
     q, k, v = _make_qkv(B, L, P, C, seed=3 + L + DH, fused=True, dev=dev)
@@ -206,6 +207,8 @@ def test_temporal_attention_backward(L, H, DH, B, P, branches):
     d_g = (torch.randn(B * P, H, L, 1, generator=g) * 0.5).to(dev, torch.float16) \
         if branches in ("o+gather", "gather", "all") else None
     d_p = (torch.randn(B * P, H, L, L, generator=g) * 0.5).to(dev, torch.float16) if branches in ("probs", "all") else None
+    if not fused:
+        q, k, v = (t.contiguous() for t in (q, k, v))
     dq, dk, dv = ops.temporal_attention_backward(q, k, v, H, scale, d_o, d_p, idx if d_g is not None else None, d_g)
     gq, gk, gv = _ref_grads(q, k, v, H, scale, d_o, d_p, idx, d_g)
     # tolerance: 2 % of the gradient's max magnitude — P, dP and dS are rounded to fp16 inside the kernel exactly where
@@ -214,6 +217,8 @@ def test_temporal_attention_backward(L, H, DH, B, P, branches):
     _close(dk, gk, name="dk")
     if d_o is not None:
         _close(dv, gv, name="dv")
+    elif fused:
+        assert dv.abs().max().item() == 0  # column block of the fused gradient buffer, zero-filled
     else:
         assert dv is None
 
@@ -222,12 +227,14 @@ def test_temporal_attention_autograd_function():
     ops, dev = _ops(), _dev()
     L, H, DH, B, P = 16, 8, 40, 1, 16
     C = H * DH
-    q, k, v = (t.clone().requires_grad_(True) for t in _make_qkv(B, L, P, C, seed=21, fused=False, dev=dev))
+    q, k, v = _make_qkv(B, L, P, C, seed=21, fused=False, dev=dev)
+    qkv = torch.cat([q, k, v], dim=-1).requires_grad_(True)  # the fused projection output the module feeds
     idx = torch.randint(0, L, (B * P, H, L, 1)).to(dev, torch.uint8)
     ref_val = torch.rand(B * P, H, L, 1).to(dev, torch.float16)
-    o, _, gathered = ops.TemporalAttention.apply(q, k, v, H, DH ** -0.5, False, idx)
+    o, _, gathered = ops.TemporalAttention.apply(qkv, H, DH ** -0.5, False, idx)
     loss = 2000 * ops.motion_loss([gathered], [ref_val]) + (o.float() ** 2).mean().half()
-    gq, gk, gv = torch.autograd.grad(loss, (q, k, v))
+    (gqkv,) = torch.autograd.grad(loss, (qkv,))
+    gq, gk, gv = gqkv[..., :C], gqkv[..., C:2 * C], gqkv[..., 2 * C:]
     # reference: fp32 autograd through the oracle's formulas
     qf, kf, vf = (_to_oracle(t.detach()).float().requires_grad_(True) for t in (q, k, v))
     probs = O.temporal_probs(qf, kf, H, DH ** -0.5)
@@ -255,3 +262,58 @@ def test_motion_loss_matches_eager_rounding():
     want_g = torch.autograd.grad(2000 * want, cur)
     for a, b in zip(grads, want_g):
         _close(a, b.float(), rel=5e-3, name="dcur")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# glue kernels of the inference passes: NHWC GroupNorm(+SiLU), LayerNorm, GEGLU
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,C,H,W", [(16, 320, 64, 64), (2, 640, 32, 32), (4, 1280, 8, 8), (3, 2560, 8, 8), (2, 1920, 16, 16),
+                                     (2, 960, 32, 32), (8, 64, 4, 4), (2, 256, 2, 2), (16, 320, 1, 1)])
+@pytest.mark.parametrize("silu", [False, True])
+def test_groupnorm_nhwc(N, C, H, W, silu):
+    """reference: InflatedGroupNorm (+ SiLU) models/resnet.py:21-29, :186-187; eps 1e-5 / 1e-6, 32 groups."""
+    ops, dev = _ops(), _dev()
+    g = torch.Generator().manual_seed(C + H)
+    x = (torch.randn(N, C, H, W, generator=g) * 3 + 1.5).to(dev, torch.float16).contiguous(memory_format=torch.channels_last)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to(dev, torch.float16)
+    b = (0.1 * torch.randn(C, generator=g)).to(dev, torch.float16)
+    with torch.no_grad():
+        y = ops.groupnorm_nhwc(x, w, b, 32, 1e-5, silu)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    ref = torch.nn.functional.group_norm(x.float(), 32, w.float(), b.float(), 1e-5)
+    eager = torch.nn.functional.group_norm(x.contiguous(), 32, w, b, 1e-5)
+    if silu:
+        ref, eager = torch.nn.functional.silu(ref), torch.nn.functional.silu(eager)
+    err = (y.float() - ref).abs().max().item()
+    err_eager = (eager.float() - ref).abs().max().item()
+    # one fp16 rounding of an O(5) value (+ one more before the fused SiLU, as the eager pair of kernels does)
+    assert err <= max(6e-3, 1.5 * err_eager), (err, err_eager)
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 320), (1024, 640), (257, 1280), (64, 64), (16, 256), (8, 2048)])
+def test_layernorm(rows, C):
+    ops, dev = _ops(), _dev()
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(2, rows, C, generator=g) * 2 + 0.5).to(dev, torch.float16)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to(dev, torch.float16)
+    b = (0.1 * torch.randn(C, generator=g)).to(dev, torch.float16)
+    with torch.no_grad():
+        y = ops.layernorm(x, w, b, 1e-5)
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), w.float(), b.float(), 1e-5)
+    eager = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5)
+    err, err_eager = (y.float() - ref).abs().max().item(), (eager.float() - ref).abs().max().item()
+    assert err <= max(4e-3, 1.5 * err_eager), (err, err_eager)
+
+
+@pytest.mark.parametrize("T,I", [(4096, 1280), (1000, 2560), (64, 5120), (16, 256)])
+def test_geglu(T, I):
+    ops, dev = _ops(), _dev()
+    g = torch.Generator().manual_seed(I)
+    x = (torch.randn(T, 2 * I, generator=g) * 2).to(dev, torch.float16)
+    with torch.no_grad():
+        y = ops.geglu(x)
+    h, gate = x.chunk(2, dim=-1)
+    eager = h * torch.nn.functional.gelu(gate)  # the eager graph of diffusers' GEGLU
+    ref = h.float() * torch.nn.functional.gelu(gate.float())
+    assert (y.float() - ref).abs().max().item() <= max(1.6e-2, 1.5 * (eager.float() - ref).abs().max().item())
+    assert (y != eager).float().mean().item() < 1e-3  # same rounding points as the eager kernels: almost always bit-equal
