@@ -120,10 +120,25 @@ int mc_add_noise(const void* x0, const void* noise, void* out, int64_t n, float 
  * workspace >= mc_groupnorm_workspace_bytes(N, G) bytes of device memory.
  */
 int64_t mc_groupnorm_workspace_bytes(int N, int G);
-int mc_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* beta, void* workspace,
-                      int64_t workspace_bytes, int N, int HW, int C, int G, float eps, int fuse_silu, void* stream);
-/* LayerNorm over the last dim (models/attention.py:189,206,212; models/motion_module.py:204,210), C % 8 == 0, C <= 2048 */
-int mc_layernorm(const void* x, void* y, const void* gamma, const void* beta, int64_t rows, int C, float eps, void* stream);
+/* chan_bias (nullable): fp16 [N / frames_per_bias_row, C] added to x before the statistics and the normalisation —
+ * the resnet's time-embedding add `hidden_states + temb` (models/resnet.py:194-195) folded into the norm that follows. */
+int mc_groupnorm_nhwc(const void* x, const void* chan_bias, int frames_per_bias_row, void* y, const void* gamma,
+                      const void* beta, void* workspace, int64_t workspace_bytes, int N, int HW, int C, int G, float eps,
+                      int fuse_silu, void* stream);
+/* LayerNorm over the last dim (models/attention.py:189,206,212; models/motion_module.py:204,210), C % 8 == 0, C <= 2048.
+ * post_add (nullable): fp16 [frames, C] added after the norm to row r at frame (r / rows_per_frame) % frames — the
+ * temporal positional encoding `x + pe[:, :f]` (models/motion_module.py:246, :281-282) on (b f)-major tokens. */
+int mc_layernorm(const void* x, void* y, const void* gamma, const void* beta, const void* post_add, int rows_per_frame,
+                 int frames, int64_t rows, int C, float eps, void* stream);
+/* Backward of the three (input gradients only: weights are frozen on this path, t2v_video_sample.py:67-68).
+ * mc_groupnorm_nhwc_stats turns the forward's workspace into stats [N, G, 2] = (mean, rstd) fp32, kept for the backward. */
+int mc_groupnorm_nhwc_stats(const void* workspace, void* stats, int N, int HW, int G, float eps, void* stream);
+int mc_groupnorm_nhwc_bwd(const void* x, const void* chan_bias, int frames_per_bias_row, const void* dz, void* dx,
+                          const void* stats, const void* gamma, const void* beta, void* workspace,
+                          int64_t workspace_bytes, int N, int HW, int C, int G, int fuse_silu, void* stream);
+int mc_layernorm_bwd(const void* x, const void* dy, void* dx, const void* gamma, int64_t rows, int C, float eps,
+                     void* stream);
+int mc_geglu_bwd(const void* in, const void* dout, void* din, int64_t T, int I, void* stream);
 /* GEGLU of diffusers-0.16 FeedForward (models/attention.py:211, models/motion_module.py:209):
  * in [T, 2I] = [h | gate] -> out [T, I] = h * gelu_erf(gate), gelu output rounded to fp16 as in the eager graph */
 int mc_geglu(const void* in, void* out, int64_t T, int I, void* stream);

@@ -23,7 +23,8 @@ _lib = None
 
 EXPORTS = ("mc_abi_version", "mc_last_error", "mc_launch_count", "mc_reset_launch_count", "mc_temporal_attn_fwd",
            "mc_temporal_attn_bwd", "mc_top1_rows", "mc_motion_loss_fwd", "mc_motion_loss_bwd", "mc_cfg_ddim_step",
-           "mc_add_noise", "mc_groupnorm_workspace_bytes", "mc_groupnorm_nhwc", "mc_layernorm", "mc_geglu")
+           "mc_add_noise", "mc_groupnorm_workspace_bytes", "mc_groupnorm_nhwc", "mc_layernorm", "mc_geglu", "mc_groupnorm_nhwc_stats", "mc_groupnorm_nhwc_bwd", "mc_layernorm_bwd",
+           "mc_geglu_bwd")
 
 
 def lib() -> ctypes.CDLL:
@@ -59,11 +60,19 @@ def lib() -> ctypes.CDLL:
     L.mc_groupnorm_workspace_bytes.restype = c_int64
     L.mc_groupnorm_workspace_bytes.argtypes = [c_int, c_int]
     L.mc_groupnorm_nhwc.restype = c_int
-    L.mc_groupnorm_nhwc.argtypes = [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, c_int, P]
+    L.mc_groupnorm_nhwc.argtypes = [P, P, c_int, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, c_int, P]
     L.mc_layernorm.restype = c_int
-    L.mc_layernorm.argtypes = [P, P, P, P, c_int64, c_int, c_float, P]
+    L.mc_layernorm.argtypes = [P, P, P, P, P, c_int, c_int, c_int64, c_int, c_float, P]
     L.mc_geglu.restype = c_int
     L.mc_geglu.argtypes = [P, P, c_int64, c_int, P]
+    L.mc_groupnorm_nhwc_stats.restype = c_int
+    L.mc_groupnorm_nhwc_stats.argtypes = [P, P, c_int, c_int, c_int, c_float, P]
+    L.mc_groupnorm_nhwc_bwd.restype = c_int
+    L.mc_groupnorm_nhwc_bwd.argtypes = [P, P, c_int, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, P]
+    L.mc_layernorm_bwd.restype = c_int
+    L.mc_layernorm_bwd.argtypes = [P, P, P, P, c_int64, c_int, c_float, P]
+    L.mc_geglu_bwd.restype = c_int
+    L.mc_geglu_bwd.argtypes = [P, P, P, c_int64, c_int, P]
     if L.mc_abi_version() != 1:
         raise MotionCloneKernelError(f"ABI version mismatch: library {L.mc_abi_version()}, binding 1")
     _lib = L

@@ -318,38 +318,115 @@ def add_noise(x0: Tensor, noise: Tensor, alpha_t: Tensor) -> Tensor:
 _gn_workspace = {}
 
 
-def fast_path_ok(x: Tensor) -> bool:
-    """The fused glue kernels serve the no-grad passes (uncond / plain steps, up-blocks beyond the guidance cut)."""
-    return x.is_cuda and x.dtype == torch.float16 and not torch.is_grad_enabled()
+def glue_kernels_ok(x: Tensor) -> bool:
+    """CUDA fp16 activations take the fused glue kernels (csrc/norm_act.cu); anything else stays on ATen."""
+    return x.is_cuda and x.dtype == torch.float16
 
 
-def groupnorm_nhwc(x: Tensor, weight: Tensor, bias: Tensor, groups: int, eps: float, silu: bool = False) -> Tensor:
-    """x: [N, C, h, w] in channels_last (physically [N, h, w, C]); returns the same format."""
-    _require(x, "x")
-    if x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last):
-        raise ValueError("groupnorm_nhwc expects a 4-D channels_last tensor")
-    N, C, H, W = x.shape
-    y = torch.empty_like(x)  # preserves channels_last
-    need = int(_lib.lib().mc_groupnorm_workspace_bytes(N, groups))
+def _workspace(x: Tensor, need: int) -> Tensor:
     key = (x.device, torch.cuda.current_stream().cuda_stream)
     ws = _gn_workspace.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=x.device)
         _gn_workspace[key] = ws
-    st = _lib.lib().mc_groupnorm_nhwc(_ptr(x), _ptr(y), _ptr(weight), _ptr(bias), _ptr(ws), ws.numel(), N, H * W, C,
-                                      groups, float(eps), int(silu), _stream())
+    return ws
+
+
+def _check_chan_bias(x: Tensor, chan_bias: Optional[Tensor]):
+    if chan_bias is None:
+        return None, 0
+    _require(chan_bias, "chan_bias")
+    chan_bias = chan_bias.contiguous()
+    if chan_bias.dim() != 2 or chan_bias.shape[1] != x.shape[1] or x.shape[0] % chan_bias.shape[0]:
+        raise ValueError("chan_bias must be [NB, C] with N divisible by NB")
+    return chan_bias, x.shape[0] // chan_bias.shape[0]
+
+
+def groupnorm_nhwc(x: Tensor, weight: Tensor, bias: Tensor, groups: int, eps: float, silu: bool = False,
+                   chan_bias: Optional[Tensor] = None, want_stats: bool = False):
+    """x: [N, C, h, w] in channels_last (physically [N, h, w, C]); returns the same format. `chan_bias` [NB, C]
+    (N % NB == 0) is added to x first, row n // (N // NB) — the resnet's time-embedding add folded in.
+    `want_stats` also returns (mean, rstd) [N, groups, 2] fp32 for the backward."""
+    _require(x, "x")
+    if x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("groupnorm_nhwc expects a 4-D channels_last tensor")
+    chan_bias, fpr = _check_chan_bias(x, chan_bias)
+    N, C, H, W = x.shape
+    y = torch.empty_like(x)  # preserves channels_last
+    ws = _workspace(x, int(_lib.lib().mc_groupnorm_workspace_bytes(N, groups)))
+    st = _lib.lib().mc_groupnorm_nhwc(_ptr(x), _ptr(chan_bias), fpr, _ptr(y), _ptr(weight), _ptr(bias), _ptr(ws),
+                                      ws.numel(), N, H * W, C, groups, float(eps), int(silu), _stream())
     _lib.check(st, "mc_groupnorm_nhwc")
-    return y
+    if not want_stats:
+        return y
+    stats = torch.empty(N, groups, 2, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().mc_groupnorm_nhwc_stats(_ptr(ws), _ptr(stats), N, H * W, groups, float(eps), _stream()),
+               "mc_groupnorm_nhwc_stats")
+    return y, stats
 
 
-def layernorm(x: Tensor, weight: Tensor, bias: Tensor, eps: float) -> Tensor:
+class GroupNormNHWCFn(torch.autograd.Function):
+    """GroupNorm(+chan_bias)(+SiLU) on channels_last with the input gradient from csrc/norm_act.cu (weights frozen)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, chan_bias, groups: int, eps: float, silu: bool):
+        y, stats = groupnorm_nhwc(x, weight, bias, groups, eps, silu, chan_bias, want_stats=True)
+        ctx.save_for_backward(x, weight, bias, chan_bias, stats)
+        ctx.groups, ctx.silu = groups, silu
+        return y
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, weight, bias, chan_bias, stats = ctx.saved_tensors
+        dz = dz.contiguous(memory_format=torch.channels_last)
+        chan_bias, fpr = _check_chan_bias(x, chan_bias)
+        N, C, H, W = x.shape
+        dx = torch.empty_like(x)
+        ws = _workspace(x, N * 64 * ctx.groups * 8)
+        st = _lib.lib().mc_groupnorm_nhwc_bwd(_ptr(x), _ptr(chan_bias), fpr, _ptr(dz), _ptr(dx), _ptr(stats), _ptr(weight),
+                                              _ptr(bias), _ptr(ws), ws.numel(), N, H * W, C, ctx.groups, int(ctx.silu),
+                                              _stream())
+        _lib.check(st, "mc_groupnorm_nhwc_bwd")
+        return dx, None, None, None, None, None, None
+
+
+def layernorm(x: Tensor, weight: Tensor, bias: Tensor, eps: float, post_add: Optional[Tensor] = None,
+              rows_per_frame: int = 0) -> Tensor:
+    """LayerNorm over the last dim; `post_add` [F, C] is added to row r at frame (r // rows_per_frame) % F (the temporal
+    positional encoding on (b f)-major tokens)."""
     _require(x, "x")
     x = x.contiguous()
     C = x.shape[-1]
     y = torch.empty_like(x)
-    st = _lib.lib().mc_layernorm(_ptr(x), _ptr(y), _ptr(weight), _ptr(bias), x.numel() // C, C, float(eps), _stream())
+    frames = 0
+    if post_add is not None:
+        _require(post_add, "post_add")
+        post_add = post_add.contiguous()
+        frames = post_add.shape[0]
+    st = _lib.lib().mc_layernorm(_ptr(x), _ptr(y), _ptr(weight), _ptr(bias), _ptr(post_add), int(rows_per_frame), frames,
+                                 x.numel() // C, C, float(eps), _stream())
     _lib.check(st, "mc_layernorm")
     return y
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps: float, post_add, rows_per_frame: int):
+        x = x.contiguous()
+        ctx.save_for_backward(x, weight)
+        ctx.eps = eps
+        return layernorm(x, weight, bias, eps, post_add, rows_per_frame)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        C = x.shape[-1]
+        dx = torch.empty_like(x)
+        st = _lib.lib().mc_layernorm_bwd(_ptr(x), _ptr(dy), _ptr(dx), _ptr(weight), x.numel() // C, C, float(ctx.eps),
+                                         _stream())
+        _lib.check(st, "mc_layernorm_bwd")
+        return dx, None, None, None, None, None
 
 
 def geglu(x: Tensor) -> Tensor:
@@ -361,3 +438,21 @@ def geglu(x: Tensor) -> Tensor:
     st = _lib.lib().mc_geglu(_ptr(x), _ptr(out), x.numel() // (2 * I), I, _stream())
     _lib.check(st, "mc_geglu")
     return out
+
+
+class GEGLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        return geglu(x)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        I = x.shape[-1] // 2
+        din = torch.empty_like(x)
+        st = _lib.lib().mc_geglu_bwd(_ptr(x), _ptr(dout), _ptr(din), x.numel() // (2 * I), I, _stream())
+        _lib.check(st, "mc_geglu_bwd")
+        return din

@@ -25,24 +25,43 @@ from torch import nn
 from . import ops
 
 
-class LayerNorm(nn.LayerNorm):
-    """nn.LayerNorm (same parameters / state-dict keys); inference passes run csrc/norm_act.cu's warp-per-row kernel."""
+def _frozen(*params) -> bool:
+    return not any(p is not None and p.requires_grad for p in params)
 
-    def forward(self, x):
-        if ops.fast_path_ok(x) and self.elementwise_affine and x.shape[-1] % 8 == 0 and x.shape[-1] <= 2048:
-            return ops.layernorm(x, self.weight, self.bias, self.eps)
-        return super().forward(x)
+
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm (same parameters / state-dict keys) on csrc/norm_act.cu's warp-per-row kernels (forward, and the
+    input gradient when the guided pass runs under autograd with frozen weights)."""
+
+    def forward(self, x, post_add=None, rows_per_frame: int = 0):
+        """post_add [F, C]: added after the norm to the rows of frame (r // rows_per_frame) % F (temporal PE)."""
+        c = x.shape[-1]
+        if ops.glue_kernels_ok(x) and self.elementwise_affine and c % 8 == 0 and c <= 1280 \
+                and _frozen(self.weight, self.bias):
+            if torch.is_grad_enabled() and x.requires_grad:
+                return ops.LayerNormFn.apply(x, self.weight, self.bias, self.eps, post_add, rows_per_frame)
+            return ops.layernorm(x, self.weight, self.bias, self.eps, post_add, rows_per_frame)
+        y = super().forward(x)
+        if post_add is not None:
+            f, c = post_add.shape
+            y = (y.view(-1, f, rows_per_frame, c) + post_add.view(1, f, 1, c)).view(y.shape)
+        return y
 
 
 class GroupNormNHWC(nn.GroupNorm):
-    """nn.GroupNorm (same parameters / state-dict keys) that reads channels_last activations directly in inference
-    passes, optionally fusing the SiLU that follows it in the resnet blocks. ATen's CUDA GroupNorm converts a
+    """nn.GroupNorm (same parameters / state-dict keys) that reads channels_last activations directly, optionally
+    fusing the time-embedding add before it and the SiLU after it (resnet blocks). ATen's CUDA GroupNorm converts a
     channels_last input to NCHW first (a copy) and hands NCHW to the next cuDNN conv (another copy)."""
 
-    def forward(self, x, silu: bool = False):
-        if x.dim() == 4 and ops.fast_path_ok(x) and x.shape[1] % 8 == 0 and x.shape[1] <= 4096 \
-                and x.is_contiguous(memory_format=torch.channels_last):
-            return ops.groupnorm_nhwc(x, self.weight, self.bias, self.num_groups, self.eps, silu)
+    def forward(self, x, silu: bool = False, chan_bias=None):
+        """chan_bias [NB, C]: per-(batch row, channel) bias added to x first (the resnet's `+ temb`)."""
+        if x.dim() == 4 and ops.glue_kernels_ok(x) and x.shape[1] % 8 == 0 and x.shape[1] <= 4096 \
+                and x.is_contiguous(memory_format=torch.channels_last) and _frozen(self.weight, self.bias, chan_bias):
+            if torch.is_grad_enabled() and x.requires_grad:
+                return ops.GroupNormNHWCFn.apply(x, self.weight, self.bias, chan_bias, self.num_groups, self.eps, silu)
+            return ops.groupnorm_nhwc(x, self.weight, self.bias, self.num_groups, self.eps, silu, chan_bias)
+        if chan_bias is not None:
+            x = x + chan_bias.repeat_interleave(x.shape[0] // chan_bias.shape[0], dim=0)[:, :, None, None]
         y = super().forward(x)
         return F.silu(y) if silu else y
 
@@ -56,7 +75,9 @@ class GEGLU(nn.Module):
 
     def forward(self, x):
         y = self.proj(x)
-        if ops.fast_path_ok(y):
+        if ops.glue_kernels_ok(y) and y.shape[-1] % 16 == 0:
+            if torch.is_grad_enabled() and y.requires_grad:
+                return ops.GEGLUFn.apply(y)
             return ops.geglu(y)  # one pass instead of chunk -> gelu -> mul (csrc/norm_act.cu)
         h, gate = y.chunk(2, dim=-1)
         return h * F.gelu(gate)
@@ -281,14 +302,14 @@ class Transformer3DModel(nn.Module):
             video_length = f
             hidden_states = hidden_states.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
         n, c, h, w = hidden_states.shape
-        residual = hidden_states
+        residual = hidden_states.permute(0, 2, 3, 1).reshape(n, h * w, c)  # token view (zero-copy when channels_last)
         t = self.norm(hidden_states).permute(0, 2, 3, 1).reshape(n, h * w, c)
         t = self._as_linear(self.proj_in, t)
         for block in self.transformer_blocks:
             # encoder_hidden_states stays [b, 77, c]: K/V are projected once per prompt, not per frame
             t = block(t, encoder_hidden_states=encoder_hidden_states, timestep=timestep, video_length=video_length)
-        t = self._as_linear(self.proj_out, t)
-        out = t.reshape(n, h, w, -1).permute(0, 3, 1, 2) + residual
+        t = self._as_linear(self.proj_out, t) + residual  # contiguous + contiguous: vectorised add
+        out = t.reshape(n, h, w, -1).permute(0, 3, 1, 2)
         if five_d:
             out = out.reshape(b, f, c, h, w).permute(0, 2, 1, 3, 4)
         return Transformer3DModelOutput(out) if return_dict else (out,)

@@ -114,7 +114,8 @@ class VersatileAttention(CrossAttention):
     def extra_repr(self):
         return f"(Module Info) Attention_Mode: {self.attention_mode}, Is_Cross_Attention: {self.is_cross_attention}"
 
-    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, video_length=None):
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, video_length=None,
+                pe_applied: bool = False):
         if self.attention_mode != "Temporal" or encoder_hidden_states is not None or self.added_kv_proj_dim is not None:
             raise NotImplementedError  # as motion_module.py:286, :298 (cross-frame text attention is never configured)
         if attention_mask is not None or self.group_norm is not None:
@@ -123,7 +124,7 @@ class VersatileAttention(CrossAttention):
         f = int(video_length)
         b = bf // f
         x = hidden_states.view(b, f, d, c)
-        if self.pos_encoder is not None:  # :281-282 — PE indexed by the frame axis
+        if self.pos_encoder is not None and not pe_applied:  # :281-282 — PE indexed by the frame axis
             x = x + self.pos_encoder.pe[0, :f].to(x.dtype).view(1, f, 1, c)
         qkv = F.linear(x, self.fused_qkv_weight())  # to_q / to_k / to_v (bias-free, :293-302) as one GEMM
         q, k, v = qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
@@ -177,10 +178,13 @@ class TemporalTransformerBlock(nn.Module):
         self.ff_norm = LayerNorm(dim)
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, video_length=None):
+        d = hidden_states.shape[1]
         for attn, norm in zip(self.attention_blocks, self.norms):
-            hidden_states = attn(norm(hidden_states),
+            # LayerNorm (:215) and the positional-encoding add (:281-282) in one pass over the tokens
+            pe = attn.pos_encoder.pe[0, :video_length].to(hidden_states.dtype) if attn.pos_encoder is not None else None
+            hidden_states = attn(norm(hidden_states, post_add=pe, rows_per_frame=d),
                                  encoder_hidden_states=encoder_hidden_states if attn.is_cross_attention else None,
-                                 video_length=video_length) + hidden_states
+                                 video_length=video_length, pe_applied=True) + hidden_states
         return self.ff(self.ff_norm(hidden_states)) + hidden_states
 
 
@@ -217,14 +221,14 @@ class TemporalTransformer3DModel(nn.Module):
             hidden_states = hidden_states.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
         assert hidden_states.dim() == 4 and video_length is not None
         n, c, h, w = hidden_states.shape
-        residual = hidden_states
+        residual = hidden_states.permute(0, 2, 3, 1).reshape(n, h * w, c)  # token view (zero-copy when channels_last)
         t = self.norm(hidden_states)
         t = t.permute(0, 2, 3, 1).reshape(n, h * w, c)  # a view when the activation is channels_last
         t = self.proj_in(t)
         for block in self.transformer_blocks:
             t = block(t, encoder_hidden_states=encoder_hidden_states, video_length=video_length)
-        t = self.proj_out(t)
-        out = t.reshape(n, h, w, c).permute(0, 3, 1, 2) + residual
+        t = self.proj_out(t) + residual
+        out = t.reshape(n, h, w, c).permute(0, 3, 1, 2)
         if five_d:
             out = out.reshape(b, f, c, h, w).permute(0, 2, 1, 3, 4)
         return out

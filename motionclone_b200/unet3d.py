@@ -55,11 +55,11 @@ class InflatedConv3d(nn.Conv2d):
 class InflatedGroupNorm(GroupNormNHWC):
     """resnet.py:21-29; 4-D channels_last inputs take the NHWC kernel (optionally with the SiLU that follows)."""
 
-    def forward(self, x, silu: bool = False):
+    def forward(self, x, silu: bool = False, chan_bias=None):
         if x.dim() == 4:
-            return super().forward(x, silu)
+            return super().forward(x, silu, chan_bias)
         x4, bf = _fold5(x)
-        return _unfold5(super().forward(x4, silu), bf)
+        return _unfold5(super().forward(x4, silu, chan_bias), bf)
 
 
 class Upsample3D(nn.Module):
@@ -130,10 +130,9 @@ class ResnetBlock3D(nn.Module):
         """x `[(b f), C, h, w]`; temb_act `[b, temb_channels]` = SiLU(time embedding) (resnet.py:192 applies the SiLU
         in every block; it is hoisted). The projection runs once per batch element and is broadcast over frames."""
         h = self.conv1(self.norm1(x, silu=True))
-        if self.time_emb_proj is not None:
-            t = self.time_emb_proj(temb_act)
-            h = h + t.repeat_interleave(x.shape[0] // t.shape[0], dim=0)[:, :, None, None]
-        h = self.conv2(self.dropout(self.norm2(h, silu=True)))
+        t = self.time_emb_proj(temb_act) if self.time_emb_proj is not None else None
+        # `hidden_states + temb` (resnet.py:194-195) is folded into norm2 (broadcast over frames and pixels)
+        h = self.conv2(self.dropout(self.norm2(h, silu=True, chan_bias=t)))
         if self.keep_hidden_state:
             self.record_hidden_state = h
         if self.conv_shortcut is not None:

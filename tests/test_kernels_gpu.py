@@ -317,3 +317,81 @@ def test_geglu(T, I):
     ref = h.float() * torch.nn.functional.gelu(gate.float())
     assert (y.float() - ref).abs().max().item() <= max(1.6e-2, 1.5 * (eager.float() - ref).abs().max().item())
     assert (y != eager).float().mean().item() < 1e-3  # same rounding points as the eager kernels: almost always bit-equal
+
+
+def test_groupnorm_with_time_embedding_bias_and_layernorm_with_positional_add():
+    """`hidden_states + temb` folded into norm2 (models/resnet.py:194-197) and `x + pe` folded into the LayerNorm that
+    precedes VersatileAttention (models/motion_module.py:215, :281-282): same rounding points as the eager ops."""
+    ops, dev = _ops(), _dev()
+    g = torch.Generator().manual_seed(3)
+    b, f, C, H, W = 2, 16, 320, 16, 16
+    x = torch.randn(b * f, C, H, W, generator=g).to(dev, torch.float16).contiguous(memory_format=torch.channels_last)
+    temb = torch.randn(b, C, generator=g).to(dev, torch.float16)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to(dev, torch.float16)
+    bb = (0.1 * torch.randn(C, generator=g)).to(dev, torch.float16)
+    with torch.no_grad():
+        y = ops.groupnorm_nhwc(x, w, bb, 32, 1e-5, True, chan_bias=temb)
+    xe = x + temb.repeat_interleave(f, dim=0)[:, :, None, None]
+    eager = torch.nn.functional.silu(torch.nn.functional.group_norm(xe.contiguous(), 32, w, bb, 1e-5))
+    ref = torch.nn.functional.silu(torch.nn.functional.group_norm(xe.float(), 32, w.float(), bb.float(), 1e-5))
+    assert (y.float() - ref).abs().max().item() <= max(6e-3, 1.5 * (eager.float() - ref).abs().max().item())
+
+    d = 64
+    t = torch.randn(b * f, d, C, generator=g).to(dev, torch.float16)
+    pe = torch.randn(f, C, generator=g).to(dev, torch.float16)
+    with torch.no_grad():
+        z = ops.layernorm(t, w, bb, 1e-5, post_add=pe, rows_per_frame=d)
+    eager = (torch.nn.functional.layer_norm(t, (C,), w, bb, 1e-5).view(b, f, d, C) + pe.view(1, f, 1, C)).view(b * f, d, C)
+    ref = (torch.nn.functional.layer_norm(t.float(), (C,), w.float(), bb.float(), 1e-5).view(b, f, d, C)
+           + pe.float().view(1, f, 1, C)).view(b * f, d, C)
+    assert (z.float() - ref).abs().max().item() <= max(6e-3, 1.5 * (eager.float() - ref).abs().max().item())
+    assert (z != eager).float().mean().item() < 2e-2
+
+
+@pytest.mark.parametrize("N,C,H,W,f", [(16, 320, 32, 32, 16), (4, 1280, 8, 8, 2), (2, 2560, 8, 8, 2), (8, 64, 4, 4, 8)])
+@pytest.mark.parametrize("silu,with_bias", [(True, True), (True, False), (False, False)])
+def test_groupnorm_nhwc_backward(N, C, H, W, f, silu, with_bias):
+    ops, dev = _ops(), _dev()
+    g = torch.Generator().manual_seed(C + H)
+    x = (torch.randn(N, C, H, W, generator=g) * 2 + 0.7).to(dev, torch.float16).contiguous(memory_format=torch.channels_last)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to(dev, torch.float16)
+    b = (0.1 * torch.randn(C, generator=g)).to(dev, torch.float16)
+    cb = torch.randn(N // f, C, generator=g).to(dev, torch.float16) if with_bias else None
+    dz = torch.randn(N, C, H, W, generator=g).to(dev, torch.float16).contiguous(memory_format=torch.channels_last)
+    xg = x.clone().requires_grad_(True)
+    y = ops.GroupNormNHWCFn.apply(xg, w, b, cb, 32, 1e-5, silu)
+    (dx,) = torch.autograd.grad(y, xg, dz)
+    assert dx.is_contiguous(memory_format=torch.channels_last)
+    xr = x.float().clone().requires_grad_(True)
+    xin = xr if cb is None else xr + cb.float().repeat_interleave(f, dim=0)[:, :, None, None]
+    yr = torch.nn.functional.group_norm(xin, 32, w.float(), b.float(), 1e-5)
+    if silu:
+        yr = torch.nn.functional.silu(yr)
+    (dr,) = torch.autograd.grad(yr, xr, dz.float())
+    assert (y.float() - yr).abs().max().item() <= 8e-3
+    _close(dx, dr, rel=1e-2, name="groupnorm dx")
+
+
+@pytest.mark.parametrize("rows,C", [(2048, 320), (300, 640), (64, 1280), (16, 64)])
+def test_layernorm_and_geglu_backward(rows, C):
+    ops, dev = _ops(), _dev()
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(2, rows, C, generator=g) * 2 + 0.3).to(dev, torch.float16)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to(dev, torch.float16)
+    b = (0.1 * torch.randn(C, generator=g)).to(dev, torch.float16)
+    dy = torch.randn(2, rows, C, generator=g).to(dev, torch.float16)
+    xg = x.clone().requires_grad_(True)
+    (dx,) = torch.autograd.grad(ops.LayerNormFn.apply(xg, w, b, 1e-5, None, 0), xg, dy)
+    xr = x.float().clone().requires_grad_(True)
+    (dr,) = torch.autograd.grad(torch.nn.functional.layer_norm(xr, (C,), w.float(), b.float(), 1e-5), xr, dy.float())
+    _close(dx, dr, rel=1e-2, name="layernorm dx")
+
+    I = C * 2
+    u = (torch.randn(rows, 2 * I, generator=g) * 1.5).to(dev, torch.float16)
+    du = torch.randn(rows, I, generator=g).to(dev, torch.float16)
+    ug = u.clone().requires_grad_(True)
+    (dg,) = torch.autograd.grad(ops.GEGLUFn.apply(ug), ug, du)
+    ur = u.float().clone().requires_grad_(True)
+    h, gate = ur.chunk(2, dim=-1)
+    (dgr,) = torch.autograd.grad(h * torch.nn.functional.gelu(gate), ur, du.float())
+    _close(dg, dgr, rel=1e-2, name="geglu din")
