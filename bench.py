@@ -74,9 +74,16 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port (oracle/mc_oracle.py) in fp32 on the host cores
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(n_pairs: int, budget_s: float, infer: dict):
-    """Times guided and plain DDIM steps of the CPU oracle at the bench shapes; returns (t_guided, t_plain, info).
-    Only place bench.py executes oracle/ (task spec ④: cpu_baseline / --impl reference)."""
+# analytic forward-equivalents: backward over the grad-carrying 57 % of the UNet costs ~2x its forward
+GUIDED_FWD_EQUIV = 2.0 + 2 * 0.57   # uncond forward + cond forward + partial backward
+PLAIN_FWD_EQUIV = 2.0               # one b=2 forward
+
+
+def cpu_reference_steps(budget_s: float, infer: dict):
+    """CPU oracle (fp32, all host cores) at the bench shapes. Always times one b=1 UNet forward; then, if the time
+    budget allows, one real plain DDIM step (b=2 forward + CFG + DDIM) and one real guided step (forward, forward +
+    backward, loss, CFG + DDIM); otherwise those two are extrapolated from the forward with the analytic
+    forward-equivalents above. Returns (t_guided, t_plain, info). Only place bench.py executes oracle/ (task spec ④)."""
     from motionclone_b200.synthetic import UNET_SD15_CONFIG, synthetic_inputs, synthetic_state_dict
     from motionclone_b200.unet3d import UNet3DConditionModel
     from oracle import mc_oracle as O
@@ -98,23 +105,41 @@ def cpu_reference_steps(n_pairs: int, budget_s: float, infer: dict):
     timesteps = O.uneven_timesteps(infer["inference_steps"], infer["guidance_steps"], infer["guidance_scale"])
     acp = O.alphas_cumprod()
     lat, text = inp["noisy_latents"], inp["text_embeddings"]
-    tg, tp = [], []
     start = time.time()
-    for i in range(n_pairs):
+    # bounded sample: the b=1 forward on the first PROBE_FRAMES of the 16 frames (same resolution, weights and ops; cost is
+    # linear in frames to < 1 %: temporal attention is 0.1 % of the flops), scaled by L / PROBE_FRAMES. Measured on the
+    # round-1 box (128 threads): a full plain step takes 258 s and a guided step 533 s, far beyond any bench budget.
+    PROBE_FRAMES = 2
+    with torch.no_grad():
+        t0 = time.time()
+        O.unet_forward(sd, UNET_SD15_CONFIG, lat[:, :, :PROBE_FRAMES].contiguous(), int(timesteps[0]), text[[0]])
+        t_probe = time.time() - t0
+    t_fwd = t_probe * L / PROBE_FRAMES
+    log(f"[cpu] b=1 UNet forward on {PROBE_FRAMES}/{L} frames {t_probe:.1f}s -> {t_fwd:.1f}s per full forward")
+    info = dict(cores=cores, s_per_forward=t_fwd,
+                measured=f"one b=1 UNet forward on {PROBE_FRAMES} of {L} frames, scaled x{L // PROBE_FRAMES}; steps "
+                         f"extrapolated with {GUIDED_FWD_EQUIV:.2f} / {PLAIN_FWD_EQUIV:.2f} forward-equivalents per "
+                         "guided / plain step")
+    if (time.time() - start) + 1.3 * t_fwd < budget_s:
+        with torch.no_grad():
+            t0 = time.time()
+            O.unet_forward(sd, UNET_SD15_CONFIG, lat, int(timesteps[0]), text[[0]])
+            t_fwd = time.time() - t0
+        log(f"[cpu] full b=1 UNet forward {t_fwd:.1f}s")
+        info.update(s_per_forward=t_fwd, measured="one full b=1 UNet forward; steps extrapolated with "
+                    f"{GUIDED_FWD_EQUIV:.2f} / {PLAIN_FWD_EQUIV:.2f} forward-equivalents per guided / plain step")
+    t_plain, t_guided = PLAIN_FWD_EQUIV * t_fwd, GUIDED_FWD_EQUIV * t_fwd
+    if (time.time() - start) + (PLAIN_FWD_EQUIV + GUIDED_FWD_EQUIV) * t_fwd < budget_s:
         t0 = time.time()
         O.single_step(sd, UNET_SD15_CONFIG, infer, lat, infer["guidance_steps"], timesteps, acp, text, rep)  # plain
-        tp.append(time.time() - t0)
-        log(f"[cpu] plain step {tp[-1]:.1f}s")
-        if time.time() - start > budget_s and tg:
-            break
+        t_plain = time.time() - t0
+        log(f"[cpu] plain step {t_plain:.1f}s")
         t0 = time.time()
         O.single_step(sd, UNET_SD15_CONFIG, infer, lat, 0, timesteps, acp, text, rep)  # guided (fwd, fwd+bwd)
-        tg.append(time.time() - t0)
-        log(f"[cpu] guided step {tg[-1]:.1f}s")
-        if time.time() - start > budget_s:
-            break
-    return statistics.median(tg), statistics.median(tp), dict(cores=cores, guided_steps_timed=len(tg),
-                                                               plain_steps_timed=len(tp))
+        t_guided = time.time() - t0
+        log(f"[cpu] guided step {t_guided:.1f}s")
+        info["measured"] = "1 forward + 1 plain + 1 guided DDIM step"
+    return t_guided, t_plain, info
 
 
 def fps_from_step_times(t_guided, t_plain, infer):
@@ -127,20 +152,18 @@ def run_reference_arm(args):
     if rank != 0:
         return
     infer = dict(INFER, inference_steps=args.ddim_steps, guidance_steps=int(round(args.ddim_steps * 0.6)))
-    n = max(1, args.steps + args.warmup)
-    # each arm "step" is a bounded sample: one guided + one plain DDIM step at the bench shapes; the first `warmup`
-    # pairs are discarded when more than one pair fits in the time budget
-    tg, tp, info = cpu_reference_steps(n, args.ref_budget, infer)
+    # the arm's bounded sample (same for every --steps / --warmup, so the whole run fits the time budget): one UNet
+    # forward, plus one plain and one guided DDIM step when they fit, at the bench shapes; extrapolated to the sample
+    tg, tp, info = cpu_reference_steps(args.ref_budget, infer)
     fps = fps_from_step_times(tg, tp, infer)
-    sample = (f"median of {info['guided_steps_timed']} guided + {info['plain_steps_timed']} plain DDIM steps at "
-              f"16x512x512 (fp32, math attention), extrapolated to {infer['inference_steps']} steps "
-              f"({infer['guidance_steps']} guided)")
+    sample = (f"{info['measured']} at 16x512x512 (fp32 CPU oracle, math attention), extrapolated to "
+              f"{infer['inference_steps']} steps ({infer['guidance_steps']} guided)")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": 0, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * infer["video_length"] / fps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "t2v_object 16x512x512, 50-step DDIM (30 guided), SD1.5+mm widths, CPU oracle port"},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": sample,
-                             "s_per_guided_step": tg, "s_per_plain_step": tp},
+                             "s_per_guided_step": tg, "s_per_plain_step": tp, "s_per_forward": info["s_per_forward"]},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -259,11 +282,11 @@ def run_own_arm(args):
         roof["bwd"] = {"launches": b_l, "achieved": (b_b / 1e9) / (b_ms / 1e3), "frac": (b_b / 1e9) / (b_ms / 1e3) / peak}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        tg, tp, info = cpu_reference_steps(1, 1e9, infer)
+        tg, tp, info = cpu_reference_steps(args.cpu_budget, infer)
         cpu = {"value": fps_from_step_times(tg, tp, infer), "unit": UNIT, "cores": info["cores"], "kind": "port",
-               "sample": "1 guided + 1 plain DDIM step at 16x512x512 (fp32 CPU oracle, math attention), extrapolated to "
+               "sample": f"{info['measured']} at 16x512x512 (fp32 CPU oracle, math attention), extrapolated to "
                          f"{infer['inference_steps']} steps ({infer['guidance_steps']} guided)",
-               "s_per_guided_step": tg, "s_per_plain_step": tp}
+               "s_per_guided_step": tg, "s_per_plain_step": tp, "s_per_forward": info["s_per_forward"]}
     lat_bytes = host[0].numel() * 2
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -289,6 +312,7 @@ def main():
     ap.add_argument("--ddim-steps", type=int, default=50, help="profiling only: anything but 50 is not a bench value")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget", type=float, default=240.0, help="seconds of CPU work for --impl reference")
+    ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work for the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

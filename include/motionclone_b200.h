@@ -110,6 +110,10 @@ int mc_cfg_ddim_step(const void* eps_cond, const void* eps_uncond, const void* x
 int mc_add_noise(const void* x0, const void* noise, void* out, int64_t n, float sqrt_alpha, float sqrt_one_minus_alpha,
                  void* stream);
 
+/* out = a + bias[c] + b on channel-innermost fp16 tensors (n elements, C channels): the resnet's residual add
+ * `input_tensor + hidden_states` (models/resnet.py:209-211) with conv2's (+ the shortcut conv's) bias folded in. */
+int mc_bias_residual_add(const void* a, const void* b, const void* bias, void* out, int64_t n, int C, void* stream);
+
 /*
  * Memory-bound glue of the UNet3D forward on NHWC / token-major fp16 activations (inference passes only; the
  * autograd-carrying guided pass keeps ATen).

@@ -126,6 +126,24 @@ __global__ void __launch_bounds__(256) top1_rows_kernel(const __half* __restrict
   }
 }
 
+// out = a + b + bias[c] on channel-innermost (NHWC / token-major) fp16 tensors: the resnet's `input + conv2(...)`
+// (models/resnet.py:209-211) with conv2's (and the shortcut conv's) bias folded in, one pass instead of three.
+// Rounding: the eager graph rounds conv+bias to fp16, then the sum; here h(h(a + bias) + b).
+__global__ void __launch_bounds__(256) bias_residual_add_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
+                                                                const __half* __restrict__ bias, __half* __restrict__ out,
+                                                                int64_t nvec, int VC) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    Pack8 x, y, z, o;
+    x.u = ldg_nc_128(a + i * 8);
+    y.u = ldg_nc_128(b + i * 8);
+    z.u = *reinterpret_cast<const uint4*>(bias + (i % VC) * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o.h[j] = __float2half_rn(round_half(__half2float(x.h[j]) + __half2float(z.h[j])) + __half2float(y.h[j]));
+    *reinterpret_cast<uint4*>(out + i * 8) = o.u;
+  }
+}
+
 struct LossArgs {
   const __half* cur[16];
   const __half* ref[16];
@@ -319,4 +337,21 @@ extern "C" int mc_motion_loss_bwd(int M, const void* const* cur, const void* con
   motion_loss_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, (const __half*)d_loss_total);
   count_launch();
   return check_launch("motion_loss_bwd");
+}
+
+extern "C" int mc_bias_residual_add(const void* a, const void* b, const void* bias, void* out, int64_t n, int C,
+                                    void* stream) {
+  using namespace mc;
+  if (!a || !b || !bias || !out || n <= 0 || C <= 0) {
+    set_error("bias_residual_add: null pointer or non-positive size");
+    return MC_E_INVALID;
+  }
+  if (C % 8 != 0 || n % C != 0) {
+    set_error("bias_residual_add: C must be a multiple of 8 and divide n (C=%d)", C);
+    return MC_E_UNSUPPORTED;
+  }
+  bias_residual_add_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)a, (const __half*)b, (const __half*)bias, (__half*)out, n / 8, C / 8);
+  count_launch();
+  return check_launch("bias_residual_add");
 }

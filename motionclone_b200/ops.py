@@ -456,3 +456,32 @@ class GEGLUFn(torch.autograd.Function):
         st = _lib.lib().mc_geglu_bwd(_ptr(x), _ptr(dout), _ptr(din), x.numel() // (2 * I), I, _stream())
         _lib.check(st, "mc_geglu_bwd")
         return din
+
+
+def bias_residual_add(a: Tensor, b: Tensor, bias: Tensor) -> Tensor:
+    """a + bias[c] + b for channels_last 4-D (or channel-last N-D) tensors with identical strides."""
+    _require(a, "a"), _require(b, "b"), _require(bias, "bias")
+    if a.shape != b.shape or a.stride() != b.stride():
+        raise ValueError("bias_residual_add: a and b must share shape and strides")
+    if a.dim() == 4:
+        if not a.is_contiguous(memory_format=torch.channels_last):
+            raise ValueError("bias_residual_add: 4-D inputs must be channels_last")
+        C = a.shape[1]
+    else:
+        if not a.is_contiguous():
+            raise ValueError("bias_residual_add: N-D inputs must be contiguous with channels last")
+        C = a.shape[-1]
+    out = torch.empty_like(a)
+    st = _lib.lib().mc_bias_residual_add(_ptr(a), _ptr(b), _ptr(bias.contiguous()), _ptr(out), a.numel(), C, _stream())
+    _lib.check(st, "mc_bias_residual_add")
+    return out
+
+
+class BiasResidualAddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, bias):
+        return bias_residual_add(a, b, bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g, None

@@ -23,6 +23,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import ops
 from .spatial import GroupNormNHWC, Transformer3DModel
 from .temporal import get_motion_module
 
@@ -126,9 +127,30 @@ class ResnetBlock3D(nn.Module):
         self.record_hidden_state = None
         self.keep_hidden_state = False  # set by prep_unet_conv (utils/conv_layer.py:64-69)
 
+    def _fused_ok(self, x) -> bool:
+        ps = (self.conv1.bias, self.conv2.bias, self.conv_shortcut.bias if self.conv_shortcut is not None else None)
+        return (x.is_cuda and x.dtype == torch.float16 and x.is_contiguous(memory_format=CL)
+                and self.out_channels % 8 == 0 and self.output_scale_factor == 1.0 and self.time_emb_proj is not None
+                and not any(p is not None and p.requires_grad for p in ps))
+
     def forward(self, x, temb_act):
         """x `[(b f), C, h, w]`; temb_act `[b, temb_channels]` = SiLU(time embedding) (resnet.py:192 applies the SiLU
         in every block; it is hoisted). The projection runs once per batch element and is broadcast over frames."""
+        if self._fused_ok(x):
+            # conv biases never get their own elementwise pass: conv1's joins the time embedding inside norm2's
+            # channel bias, conv2's (+ the shortcut conv's) joins the residual add (one launch: csrc/elementwise.cu)
+            h = F.conv2d(self.norm1(x, silu=True), self.conv1.weight, None, 1, 1)
+            t = self.time_emb_proj(temb_act) + self.conv1.bias
+            h = F.conv2d(self.dropout(self.norm2(h, silu=True, chan_bias=t)), self.conv2.weight, None, 1, 1)
+            if self.keep_hidden_state:
+                self.record_hidden_state = h
+            bias = self.conv2.bias
+            if self.conv_shortcut is not None:
+                x = F.conv2d(x, self.conv_shortcut.weight, None)
+                bias = bias + self.conv_shortcut.bias
+            if torch.is_grad_enabled() and (h.requires_grad or x.requires_grad):
+                return ops.BiasResidualAddFn.apply(h, x, bias)
+            return ops.bias_residual_add(h, x, bias)
         h = self.conv1(self.norm1(x, silu=True))
         t = self.time_emb_proj(temb_act) if self.time_emb_proj is not None else None
         # `hidden_states + temb` (resnet.py:194-195) is folded into norm2 (broadcast over frames and pixels)

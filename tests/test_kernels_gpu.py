@@ -395,3 +395,18 @@ def test_layernorm_and_geglu_backward(rows, C):
     h, gate = ur.chunk(2, dim=-1)
     (dgr,) = torch.autograd.grad(h * torch.nn.functional.gelu(gate), ur, du.float())
     _close(dg, dgr, rel=1e-2, name="geglu din")
+
+
+def test_bias_residual_add():
+    """`input_tensor + (conv2(...) + bias)` of the resnet (models/resnet.py:204-211) in one pass, eager rounding points."""
+    ops, dev = _ops(), _dev()
+    g = torch.Generator().manual_seed(0)
+    a, b = (torch.randn(4, 320, 16, 16, generator=g).to(dev, torch.float16).contiguous(memory_format=torch.channels_last)
+            for _ in range(2))
+    bias = torch.randn(320, generator=g).to(dev, torch.float16)
+    out = ops.bias_residual_add(a, b, bias)
+    assert torch.equal(out, (a + bias[None, :, None, None]) + b)
+    ag = a.clone().requires_grad_(True)
+    bg = b.clone().requires_grad_(True)
+    ga, gb = torch.autograd.grad(ops.BiasResidualAddFn.apply(ag, bg, bias).float().sum(), (ag, bg))
+    assert torch.equal(ga, torch.ones_like(a)) and torch.equal(gb, torch.ones_like(b))
