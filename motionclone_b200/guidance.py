@@ -72,6 +72,28 @@ def _set_processor_mode(self, mode: Optional[str], ref_idx: Optional[Dict[str, t
         m.processor.ref_idx = None if ref_idx is None else ref_idx[name]
 
 
+def _controlnet_residuals(self, latents, step_t, text, images):
+    """SparseCtrl call of :46-72 / :176-197: zero-filled condition + mask with the conditioned frames set, then the
+    controlnet under no_grad. The assembled condition is cached (it does not change between steps); so is its embedding
+    inside the controlnet."""
+    cfg = self.input_config
+    idx = list(_cfg_get(cfg, "image_index"))
+    key = (images.data_ptr(), images._version, tuple(images.shape), latents.shape[2], tuple(idx))
+    cache = getattr(self, "_cn_cond_cache", None)
+    if cache is None or cache[0] != key:
+        shp = list(images.shape)
+        shp[2] = latents.shape[2]
+        cond = torch.zeros(shp, device=latents.device, dtype=latents.dtype)
+        mask = torch.zeros([shp[0], 1] + shp[2:], device=latents.device, dtype=latents.dtype)
+        cond[:, :, idx] = images.to(device=latents.device, dtype=latents.dtype)
+        mask[:, :, idx] = 1
+        self._cn_cond_cache = cache = (key, cond, mask)
+    with torch.no_grad():
+        return self.controlnet(latents, step_t, encoder_hidden_states=text, controlnet_cond=cache[1],
+                               conditioning_mask=cache[2], conditioning_scale=_cfg_get(cfg, "controlnet_scale"),
+                               guess_mode=False, return_dict=False)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # 1. add_noise
 # ----------------------------------------------------------------------------------------------------------------
@@ -104,12 +126,23 @@ def obtain_motion_representation(self, generator=None, motion_representation_pat
         noise = torch.randn(video_latents.shape, generator=generator, device=video_latents.device,
                             dtype=video_latents.dtype)
     noisy_latents = self.add_noise(step_t, video_latents, noise.to(video_latents))
-    if use_controlnet:
-        raise NotImplementedError("SparseCtrl conditioning is the next §8 row (SURVEY.md §8f-3)")
+    down_res = mid_res = None
+    if use_controlnet:  # :46-72 — the condition is taken from the CLIP itself at `image_index`
+        idx = list(_cfg_get(cfg, "image_index"))
+        if self.controlnet.use_simplified_condition_embedding:
+            images = video_latents[:, :, idx]
+        else:
+            pixels = _cfg_get(cfg, "video_pixels")  # [f, 3, H, W] in [-1, 1] == video_preprocess output (:29)
+            if pixels is None:
+                raise NotImplementedError("video decode is outside the hot path: pass input_config.video_pixels")
+            pixels = pixels.to(device=self.device, dtype=self.unet.dtype)
+            images = ((pixels.unsqueeze(0).permute(0, 2, 1, 3, 4) + 1) / 2)[:, :, idx]
+        down_res, mid_res = _controlnet_residuals(self, noisy_latents, step_t, uncond.to(noisy_latents), images)
 
     _set_processor_mode(self, "top1")
     self.unet(noisy_latents, step_t, encoder_hidden_states=uncond.to(noisy_latents), return_dict=False,
-              only_motion_feature=True)
+              only_motion_feature=True, down_block_additional_residuals=down_res,
+              mid_block_additional_residual=mid_res)
     motion_representation = {}
     for name, m in guided_modules(self).items():
         val, idx = m.processor.top1  # fused top-1 epilogue == topk(k=1) + uint8 cast of :79
@@ -180,8 +213,13 @@ def sample_video(self, eta: float = 0.0, generator=None, noisy_latents: Optional
     final latents `[1, 4, f, h/8, w/8]`."""
     cfg = self.input_config
     self.add_controlnet = add_controlnet
-    if add_controlnet:
-        raise NotImplementedError("SparseCtrl conditioning is the next §8 row (SURVEY.md §8f-3)")
+    if add_controlnet:  # :111-128 — image files + VAE encode are off the path: the caller passes their result
+        images = _cfg_get(cfg, "controlnet_images")
+        if images is None:
+            raise NotImplementedError("image loading + VAE encode are outside the hot path: pass "
+                                      "input_config.controlnet_images [1, c, n_images, h, w] (latents x 0.18215 for the "
+                                      "simplified embedding, RGB in [0, 1] otherwise)")
+        self.controlnet_images = images.to(device=self.device, dtype=self.unet.dtype)
     batch_size = 1
     device = self._execution_device
     self.text_embeddings = self._encode_prompt(_cfg_get(cfg, "new_prompt"), device, 1, True,
@@ -207,10 +245,12 @@ def sample_video(self, eta: float = 0.0, generator=None, noisy_latents: Optional
 
 
 def single_step_video(self, noisy_latents, step_index, step_t, extra_step_kwargs):
-    """:173-257 (controlnet branch: next §8 row)."""
+    """:173-257."""
     cfg = self.input_config
-    if getattr(self, "add_controlnet", False):
-        raise NotImplementedError("SparseCtrl conditioning is the next §8 row (SURVEY.md §8f-3)")
+    down = mid = None
+    if getattr(self, "add_controlnet", False):  # :176-197: SparseCtrl at b=2 ([uncond, cond]) under no_grad
+        down, mid = _controlnet_residuals(self, noisy_latents.expand(2, -1, -1, -1, -1), step_t, self.text_embeddings,
+                                          self.controlnet_images)
     guidance_steps = _cfg_get(cfg, "guidance_steps")
     cfg_scale = _cfg_get(cfg, "cfg_scale")
     if step_index < guidance_steps:
@@ -219,9 +259,13 @@ def single_step_video(self, noisy_latents, step_index, step_t, extra_step_kwargs
         control_latents.requires_grad = True
         with torch.no_grad():
             _set_processor_mode(self, None)
-            eps_u = self.unet(noisy_latents, step_t, encoder_hidden_states=self.text_embeddings[[0]]).sample
+            eps_u = self.unet(noisy_latents, step_t, encoder_hidden_states=self.text_embeddings[[0]],
+                              down_block_additional_residuals=None if down is None else [r[0:1] for r in down],
+                              mid_block_additional_residual=None if mid is None else mid[0:1]).sample
         _set_processor_mode(self, "gather", {k: v[1] for k, v in rep.items()})
-        eps_c = self.unet(control_latents, step_t, encoder_hidden_states=self.text_embeddings[[1]]).sample
+        eps_c = self.unet(control_latents, step_t, encoder_hidden_states=self.text_embeddings[[1]],
+                          down_block_additional_residuals=None if down is None else [r[1:2] for r in down],
+                          mid_block_additional_residual=None if mid is None else mid[1:2]).sample
         gathered = {name: m.processor.gathered for name, m in guided_modules(self).items()}
         loss_motion = self.motion_scale * self.compute_temp_loss(gathered)
         if step_index < _cfg_get(cfg, "warm_up_steps"):  # :228-230
@@ -238,8 +282,8 @@ def single_step_video(self, noisy_latents, step_index, step_t, extra_step_kwargs
         return out.detach()
     with torch.no_grad():
         _set_processor_mode(self, None)
-        pair = self.unet(noisy_latents.expand(2, -1, -1, -1, -1), step_t,
-                         encoder_hidden_states=self.text_embeddings).sample
+        pair = self.unet(noisy_latents.expand(2, -1, -1, -1, -1), step_t, encoder_hidden_states=self.text_embeddings,
+                         down_block_additional_residuals=down, mid_block_additional_residual=mid).sample
         out = self.scheduler.customized_step_fused(pair[[1]], pair[[0]], cfg_scale, step_index, noisy_latents,
                                                    score=None, **extra_step_kwargs)
     return out.detach()
@@ -359,6 +403,9 @@ def bind_motionclone(pipeline, config):
     pipeline.obtain_motion_representation = obtain_motion_representation.__get__(pipeline)
     for p in pipeline.unet.parameters():
         p.requires_grad = False
+    if getattr(pipeline, "controlnet", None) is not None:  # i2v_video_sample.py:96-97
+        for p in pipeline.controlnet.parameters():
+            p.requires_grad = False
     pipeline.input_config, pipeline.unet.input_config = config, config
     pipeline.unet = prep_unet_attention(pipeline.unet, _cfg_get(config, "motion_guidance_blocks"))
     pipeline.unet = prep_unet_conv(pipeline.unet)

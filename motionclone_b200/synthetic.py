@@ -80,6 +80,31 @@ def synthetic_normal(tag: str, shape: Sequence[int], seed: int) -> torch.Tensor:
     return torch.from_numpy(_rng("input:" + tag, seed).standard_normal(size=shape, dtype=np.float32))
 
 
+# configs/sparsectrl/latent_condition.yaml / image_condition.yaml (controlnet_additional_kwargs)
+_SPARSECTRL_COMMON = dict(set_noisy_sample_input_to_zero=True, use_motion_module=True, motion_module_resolutions=[1, 2, 4, 8],
+                          motion_module_mid_block=False, motion_module_type="Vanilla",
+                          motion_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1,
+                                                    attention_block_types=["Temporal_Self"],
+                                                    temporal_position_encoding=True,
+                                                    temporal_position_encoding_max_len=32, temporal_attention_dim_div=1))
+SPARSECTRL_LATENT_KWARGS = dict(_SPARSECTRL_COMMON, use_simplified_condition_embedding=True, conditioning_channels=4)
+SPARSECTRL_IMAGE_KWARGS = dict(_SPARSECTRL_COMMON, use_simplified_condition_embedding=False, conditioning_channels=3)
+
+
+def synthetic_condition(kind: str, n_images: int, height: int, width: int, video_length: int, seed: int):
+    """Synthetic SparseCtrl inputs: 'latent' -> condition latents [n, 4, h/8, w/8] ~ N(0,1) (stands in for the VAE encode
+    of the condition images); 'image' -> RGB condition images [n, 3, h, w] quantised to uint8 levels in [0, 1] (what
+    ToTensor() yields, motionclone_functions.py:112-117) and clip pixels [f, 3, h, w] in [-1, 1]."""
+    if kind == "latent":
+        return dict(cond_latents=synthetic_normal("cond_latents", (n_images, 4, height // 8, width // 8), seed))
+    u8 = np.random.Generator(np.random.Philox(key=[zlib.crc32(b"cond_images"), seed])).integers(
+        0, 256, size=(n_images, 3, height, width), dtype=np.uint8)
+    pix = np.random.Generator(np.random.Philox(key=[zlib.crc32(b"clip_pixels"), seed])).uniform(
+        -1.0, 1.0, size=(video_length, 3, height, width)).astype(np.float32)
+    return dict(cond_images_u8=torch.from_numpy(u8), cond_images=torch.from_numpy(u8).float() / 255.0,
+                clip_pixels=torch.from_numpy(pix))
+
+
 def synthetic_inputs(video_length: int, height: int, width: int, cross_attention_dim: int, seed: int = 42):
     """latents seed s, reference-clip latent s+1, clip noise s+2, text embeddings s+3."""
     shp = (1, 4, video_length, height // 8, width // 8)

@@ -13,7 +13,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from motionclone_b200.synthetic import UNET_SD15_CONFIG, UNET_TINY_CONFIG, synthetic_inputs  # noqa: E402
+from motionclone_b200.synthetic import (SPARSECTRL_IMAGE_KWARGS, SPARSECTRL_LATENT_KWARGS, UNET_SD15_CONFIG,  # noqa: E402
+                                        UNET_TINY_CONFIG, synthetic_condition, synthetic_inputs)
 from oracle.ref_runner import run_reference  # noqa: E402
 
 BASE = dict(cfg_scale=7.5, negative_prompt="", warm_up_steps=10, cool_up_steps=10, motion_guidance_weight=2000,
@@ -25,6 +26,11 @@ CASES = {
                            width=128), 42),
     "tiny16": ("tiny", dict(BASE, inference_steps=5, guidance_steps=3, guidance_scale=0.4, video_length=16, height=128,
                             width=128, warm_up_steps=2, cool_up_steps=2), 52),
+    # SparseCtrl (BASELINE.json configs[3], [4] topology at tiny widths): latent condition (i2v_rgb) / image condition (i2v_sketch)
+    "tiny8_i2v_latent": ("tiny", dict(BASE, inference_steps=4, guidance_steps=2, guidance_scale=0.3, video_length=8, height=128,
+                                      width=128, image_index=[0], controlnet_scale=1.0, sparsectrl="latent"), 62),
+    "tiny8_i2v_image": ("tiny", dict(BASE, inference_steps=4, guidance_steps=2, guidance_scale=0.3, video_length=8, height=128,
+                                     width=128, image_index=[0, 5], controlnet_scale=0.8, sparsectrl="image"), 72),
     # BASELINE.json configs[0]: t2v_camera, 8x256x256, 10 DDIM steps, SD1.5 widths (plumbing case, CPU-runnable)
     "c1": ("sd15", dict(BASE, inference_steps=10, guidance_steps=5, guidance_scale=0.3, video_length=8, height=256,
                         width=256), 42),
@@ -38,7 +44,29 @@ def main(names):
         ucfg = UNET_TINY_CONFIG if ucfg_name == "tiny" else UNET_SD15_CONFIG
         inp = synthetic_inputs(icfg["video_length"], icfg["height"], icfg["width"], ucfg["cross_attention_dim"], seed)
         t0 = time.time()
-        out, pipe = run_reference(ucfg, icfg, inp, f"/tmp/_golden_{name}.pt", weight_seed=42)
+        cn_kwargs = None
+        if icfg.get("sparsectrl"):
+            kind = icfg["sparsectrl"]
+            cn_kwargs = SPARSECTRL_LATENT_KWARGS if kind == "latent" else SPARSECTRL_IMAGE_KWARGS
+            cond = synthetic_condition(kind, len(icfg["image_index"]), icfg["height"], icfg["width"], icfg["video_length"],
+                                       seed + 5)
+            inp.update(cond)
+            paths = []
+            if kind == "image":  # the reference opens image files (motionclone_functions.py:117): write lossless PNGs
+                from PIL import Image
+                for j, im in enumerate(cond["cond_images_u8"]):
+                    pth = f"/tmp/_golden_{name}_cond{j}.png"
+                    Image.fromarray(im.permute(1, 2, 0).numpy()).save(pth)
+                    paths.append(pth)
+            else:  # latent kind: the stub VAE returns the preset latents; the files only need to exist and open
+                from PIL import Image
+                for j in range(len(icfg["image_index"])):
+                    pth = f"/tmp/_golden_{name}_cond{j}.png"
+                    Image.fromarray(np.zeros((icfg["height"], icfg["width"], 3), dtype=np.uint8)).save(pth)
+                    paths.append(pth)
+            icfg = dict(icfg, condition_image_path_list=paths)
+        out, pipe = run_reference(ucfg, icfg, inp, f"/tmp/_golden_{name}.pt", weight_seed=42, controlnet_kwargs=cn_kwargs)
+        icfg = {k: v for k, v in icfg.items() if k != "condition_image_path_list"}
         arrays = {k: (v.numpy() if torch.is_tensor(v) else np.array(v)) for k, v in out.items()}
         arrays["meta"] = np.array(json.dumps(dict(case=name, unet=ucfg_name, infer=icfg, input_seed=seed,
                                                    weight_seed=42, torch=torch.__version__,
@@ -54,6 +82,10 @@ def main(names):
         if name != "c1":
             shapes = {k: list(v.shape) for k, v in pipe.unet.state_dict().items()}
             with open(os.path.join(ROOT, "tests", "golden", f"ref_state_dict_shapes_{ucfg_name}.json"), "w") as f:
+                json.dump(shapes, f, indent=0)
+        if pipe.controlnet is not None:
+            shapes = {k: list(v.shape) for k, v in pipe.controlnet.state_dict().items()}
+            with open(os.path.join(ROOT, "tests", "golden", f"ref_state_dict_shapes_controlnet_{icfg['sparsectrl']}.json"), "w") as f:
                 json.dump(shapes, f, indent=0)
         del pipe, out
 

@@ -320,7 +320,10 @@ def _motion_module(sd: _SD, x: Tensor, heads: int, groups: int, pes: Dict[int, T
     blk = tt.sub("transformer_blocks.0")
     if c not in pes:
         pes[c] = positional_encoding(c).to(device=x.device)
-    for i in range(2):  # attention_block_types = (Temporal_Self, Temporal_Self)
+    n_attn = 0
+    while blk.has(f"attention_blocks.{n_attn}.to_q.weight"):
+        n_attn += 1
+    for i in range(n_attn):  # UNet: (Temporal_Self, Temporal_Self); SparseCtrl: (Temporal_Self,) — configs/sparsectrl/*.yaml:14
         n = F.layer_norm(t, (c,), blk[f"norms.{i}.weight"], blk[f"norms.{i}.bias"], 1e-5)
         aname = f"{name}.temporal_transformer.transformer_blocks.0.attention_blocks.{i}"
         t = _versatile_attention(blk.sub(f"attention_blocks.{i}"), n, f, heads, pes[c],
@@ -332,9 +335,97 @@ def _motion_module(sd: _SD, x: Tensor, heads: int, groups: int, pes: Dict[int, T
     return out.reshape(b, f, c, h, w).permute(0, 2, 1, 3, 4)
 
 
+def _down_and_mid(sd: _SD, cfg: dict, x: Tensor, emb: Tensor, text: Tensor, mm_heads: int, pes: dict,
+                  record: Optional[dict], guided, prefix: str = ""):
+    """conv_in output -> (mid-block output, skip list). Shared by the UNet (models/unet_blocks.py:382-421, :493-521,
+    :271-278) and SparseCtrl (models/sparse_controlnet.py:529-552), which reuse the same block classes."""
+    groups, eps = cfg["norm_num_groups"], cfg["norm_eps"]
+    heads = cfg["attention_head_dim"]  # used as the head COUNT (models/unet_blocks.py:343-344)
+    chans = cfg["block_out_channels"]
+    skips = [x]
+    for i, btype in enumerate(cfg["down_block_types"]):
+        blk = sd.sub(f"down_blocks.{i}")
+        for j in range(cfg["layers_per_block"]):
+            x = _resnet(blk.sub(f"resnets.{j}"), x, emb, groups, eps)
+            if btype.startswith("CrossAttn"):
+                x = _spatial_transformer(blk.sub(f"attentions.{j}"), x, text, heads, groups)
+            mname = f"{prefix}down_blocks.{i}.motion_modules.{j}"
+            x = _motion_module(blk.sub(f"motion_modules.{j}"), x, mm_heads, groups, pes, record, mname, guided(mname))
+            skips.append(x)
+        if i < len(chans) - 1:
+            x = _conv(blk, "downsamplers.0.conv", x, stride=2, padding=1)
+            skips.append(x)
+    mid = sd.sub("mid_block")  # no motion module: motion_module_mid_block=false
+    x = _resnet(mid.sub("resnets.0"), x, emb, groups, eps)
+    x = _spatial_transformer(mid.sub("attentions.0"), x, text, heads, groups)
+    x = _resnet(mid.sub("resnets.1"), x, emb, groups, eps)
+    return x, skips
+
+
+def _time_embedding(sd: _SD, timestep, sample: Tensor, dim: int) -> Tensor:
+    if not torch.is_tensor(timestep):
+        timestep = torch.tensor([timestep], dtype=torch.int64, device=sample.device)
+    elif timestep.dim() == 0:
+        timestep = timestep[None].to(sample.device)
+    timestep = timestep.expand(sample.shape[0])
+    t_emb = timestep_embedding(timestep, dim).to(sample.dtype)
+    te = sd.sub("time_embedding")
+    return te.linear("linear_2", F.silu(te.linear("linear_1", t_emb)))
+
+
+def controlnet_forward(sd_flat: Dict[str, Tensor], cfg: dict, cn_kwargs: dict, sample: Tensor, timestep, text: Tensor,
+                       controlnet_cond: Tensor, conditioning_mask: Tensor, conditioning_scale: float = 1.0):
+    """models/sparse_controlnet.py:450-587 (SparseControlNetModel.forward; guess_mode False, no global pooling).
+
+    `cfg` is the UNet config it was built from (from_unet, :317-370); `cn_kwargs` the controlnet_additional_kwargs of
+    configs/sparsectrl/*.yaml. Returns (12 down residuals, mid residual), each `[b, c, f, h, w]`.
+    """
+    sd = _SD(sd_flat)
+    chans = cfg["block_out_channels"]
+    mm_heads = cn_kwargs["motion_module_kwargs"]["num_attention_heads"]
+    text = text.repeat(sample.shape[0] // text.shape[0], 1, 1)  # :488
+    emb = _time_embedding(sd, timestep, sample, chans[0]).to(sample.dtype)
+    if cn_kwargs.get("set_noisy_sample_input_to_zero", False):  # :516-518: conv_in(0) == bias
+        b, _, f, h, w = sample.shape
+        x = sd["conv_in.bias"].reshape(1, -1, 1, 1, 1).expand(b, -1, f, h, w)
+    else:
+        x = _conv(sd, "conv_in", sample)
+    cond = torch.cat([controlnet_cond, conditioning_mask], dim=1).to(torch.float16)  # :522-523 (fp16 hard-coded)
+    ce = sd.sub("controlnet_cond_embedding")
+    if cn_kwargs.get("use_simplified_condition_embedding", False):  # :181-184: one zero-initialised 3x3 conv
+        e = _frames_op(lambda t: F.conv2d(t, sd["controlnet_cond_embedding.weight"], sd["controlnet_cond_embedding.bias"],
+                                          padding=1), cond)
+    else:  # SparseControlNetConditioningEmbedding, :49-82
+        e = F.silu(_conv(ce, "conv_in", cond))
+        n_blocks = 0
+        while ce.has(f"blocks.{n_blocks}.weight"):
+            n_blocks += 1
+        for i in range(n_blocks):
+            e = F.silu(_conv(ce, f"blocks.{i}", e, stride=2 if i % 2 == 1 else 1))
+        e = _conv(ce, "conv_out", e)
+    x = x + e  # :527
+    x, skips = _down_and_mid(sd, cfg, x, emb, text, mm_heads, {}, None, lambda n: False)
+    down = [_conv(sd, f"controlnet_down_blocks.{i}", s_, padding=0) * conditioning_scale for i, s_ in enumerate(skips)]
+    mid = _conv(sd, "controlnet_mid_block", x, padding=0) * conditioning_scale
+    return down, mid
+
+
+def controlnet_condition(images: Tensor, image_index: Sequence[int], video_length: int, dtype, device):
+    """utils/motionclone_functions.py:54-63 / :178-188: zero-filled condition + 1-channel mask with the given frames set.
+    images `[1, c, n_img, h, w]`."""
+    shp = list(images.shape)
+    shp[2] = video_length
+    cond = torch.zeros(shp, dtype=dtype, device=device)
+    mask = torch.zeros([shp[0], 1] + shp[2:], dtype=dtype, device=device)
+    cond[:, :, list(image_index)] = images.to(device=device, dtype=dtype)
+    mask[:, :, list(image_index)] = 1
+    return cond, mask
+
+
 def unet_forward(sd_flat: Dict[str, Tensor], cfg: dict, sample: Tensor, timestep, text: Tensor,
                  record: Optional[dict] = None, guidance_blocks: Sequence[str] = ("up_blocks.1",),
-                 only_motion_feature: bool = False):
+                 only_motion_feature: bool = False, down_residuals: Optional[Sequence[Tensor]] = None,
+                 mid_residual: Optional[Tensor] = None):
     """utils/motionclone_functions.py:478-662 (unet_customized_forward) over the topology of models/unet.py:42-249.
 
     `record` (dict) receives {module_name: (q, k)} for VersatileAttention modules whose name contains one of
@@ -349,34 +440,15 @@ def unet_forward(sd_flat: Dict[str, Tensor], cfg: dict, sample: Tensor, timestep
     pes: Dict[int, Tensor] = {}
     guided = lambda n: any(g in n for g in guidance_blocks)  # noqa: E731  (utils/util.py:434-440)
 
-    if not torch.is_tensor(timestep):
-        timestep = torch.tensor([timestep], dtype=torch.int64, device=sample.device)
-    elif timestep.dim() == 0:
-        timestep = timestep[None].to(sample.device)
-    timestep = timestep.expand(sample.shape[0])
-    t_emb = timestep_embedding(timestep, chans[0]).to(sample.dtype)  # :545-550
-    te = sd.sub("time_embedding")
-    emb = te.linear("linear_2", F.silu(te.linear("linear_1", t_emb)))
+    emb = _time_embedding(sd, timestep, sample, chans[0])  # :545-551
 
     x = _conv(sd, "conv_in", sample)
-    skips = [x]
-    for i, btype in enumerate(cfg["down_block_types"]):  # models/unet_blocks.py:382-421, :493-521
-        blk = sd.sub(f"down_blocks.{i}")
-        for j in range(cfg["layers_per_block"]):
-            x = _resnet(blk.sub(f"resnets.{j}"), x, emb, groups, eps)
-            if btype.startswith("CrossAttn"):
-                x = _spatial_transformer(blk.sub(f"attentions.{j}"), x, text, heads, groups)
-            mname = f"down_blocks.{i}.motion_modules.{j}"
-            x = _motion_module(blk.sub(f"motion_modules.{j}"), x, mm_heads, groups, pes, record, mname, guided(mname))
-            skips.append(x)
-        if i < len(chans) - 1:
-            x = _conv(blk, "downsamplers.0.conv", x, stride=2, padding=1)
-            skips.append(x)
-
-    mid = sd.sub("mid_block")  # models/unet_blocks.py:271-278 (no motion module: motion_module_mid_block=false)
-    x = _resnet(mid.sub("resnets.0"), x, emb, groups, eps)
-    x = _spatial_transformer(mid.sub("attentions.0"), x, text, heads, groups)
-    x = _resnet(mid.sub("resnets.1"), x, emb, groups, eps)
+    x, skips = _down_and_mid(sd, cfg, x, emb, text, mm_heads, pes, record, guided)
+    # NOTE: the reference adds the mid residual AFTER the mid block and the down residuals to the skip list (:582-598)
+    if down_residuals is not None:
+        skips = [s_ + (r.unsqueeze(2) if r.dim() == 4 else r) for s_, r in zip(skips, down_residuals)]
+    if mid_residual is not None:
+        x = x + (mid_residual.unsqueeze(2) if mid_residual.dim() == 4 else mid_residual)
 
     cut = int(guidance_blocks[-1].split(".")[-1])
     for i, btype in enumerate(cfg["up_block_types"]):  # models/unet_blocks.py:621-667, :735-760
@@ -412,33 +484,60 @@ def record_to_probs(record: Dict[str, Tuple[Tensor, Tensor]], heads: int) -> Dic
     return out
 
 
+def _controlnet_residuals(cn: dict, cfg: dict, latents: Tensor, t: int, text: Tensor, images: Tensor):
+    """utils/motionclone_functions.py:46-72 / :176-197. cn = dict(sd, kwargs, image_index, scale)."""
+    cond, mask = controlnet_condition(images, cn["image_index"], latents.shape[2], latents.dtype, latents.device)
+    with torch.no_grad():
+        return controlnet_forward(cn["sd"], cfg, cn["kwargs"], latents, t, text, cond, mask, cn["scale"])
+
+
 @torch.no_grad()
 def obtain_motion_representation(sd, cfg, clip_latents: Tensor, clip_noise: Tensor, uncond_text: Tensor,
-                                 add_noise_step: int = 400, guidance_blocks=("up_blocks.1",)):
-    """utils/motionclone_functions.py:25-82 with the VAE/CLIP outputs given (synthetic)."""
+                                 add_noise_step: int = 400, guidance_blocks=("up_blocks.1",),
+                                 controlnet: Optional[dict] = None, clip_pixels: Optional[Tensor] = None):
+    """utils/motionclone_functions.py:25-82 with the VAE/CLIP outputs given (synthetic). With `controlnet`
+    (dict(sd, kwargs, image_index, scale)) the condition comes from the CLIP itself: its latents (simplified
+    embedding, :49) or its pixels `[f, 3, H, W]` in [-1, 1] mapped to [0, 1] (:51-52)."""
     acp = alphas_cumprod()
     noisy = add_noise(acp, int(add_noise_step), clip_latents, clip_noise)
     record: Dict[str, Tuple[Tensor, Tensor]] = {}
+    down = mid = None
+    if controlnet is not None:
+        if controlnet["kwargs"].get("use_simplified_condition_embedding", False):
+            images = clip_latents[:, :, list(controlnet["image_index"])]
+        else:
+            pix = (clip_pixels.unsqueeze(0).permute(0, 2, 1, 3, 4).to(clip_latents) + 1) / 2
+            images = pix[:, :, list(controlnet["image_index"])]
+        down, mid = _controlnet_residuals(controlnet, cfg, noisy, int(add_noise_step), uncond_text, images)
     unet_forward(sd, cfg, noisy, int(add_noise_step), uncond_text, record=record, guidance_blocks=guidance_blocks,
-                 only_motion_feature=True)
+                 only_motion_feature=True, down_residuals=down, mid_residual=mid)
     probs = record_to_probs(record, cfg["motion_module_kwargs"]["num_attention_heads"])
     return {k: list(top1(p)) for k, p in probs.items()}, probs
 
 
 def single_step(sd, cfg, icfg: dict, latents: Tensor, step_index: int, timesteps, acp: Tensor, text: Tensor,
-                representation, reciprocal_div: bool = False, stats: Optional[dict] = None) -> Tensor:
-    """utils/motionclone_functions.py:173-257 (single_step_video), controlnet off."""
+                representation, reciprocal_div: bool = False, stats: Optional[dict] = None,
+                controlnet: Optional[dict] = None) -> Tensor:
+    """utils/motionclone_functions.py:173-257 (single_step_video). `controlnet` = dict(sd, kwargs, image_index, scale,
+    images `[1, c, n_img, h, w]`) runs SparseCtrl at b=2 under no_grad (:176-197) and splits its residuals per pass."""
     t = int(timesteps[step_index])
+    du = dc = dpair = mu = mc_ = mpair = None
+    if controlnet is not None:
+        dpair, mpair = _controlnet_residuals(controlnet, cfg, latents.expand(2, -1, -1, -1, -1), t, text,
+                                             controlnet["images"])
+        du, dc = [r[[0]].detach() for r in dpair], [r[[1]].detach() for r in dpair]  # :205-208
+        mu, mc_ = mpair[[0]].detach(), mpair[[1]].detach()
     a_t, a_prev = ddim_scalars(acp, timesteps, step_index)
     mm_heads = cfg["motion_module_kwargs"]["num_attention_heads"]
     gb = tuple(icfg["motion_guidance_blocks"])
     if step_index < icfg["guidance_steps"]:
         control = latents.clone().detach().requires_grad_(True)
         with torch.no_grad():
-            eps_u = unet_forward(sd, cfg, latents, t, text[[0]], guidance_blocks=gb)
+            eps_u = unet_forward(sd, cfg, latents, t, text[[0]], guidance_blocks=gb, down_residuals=du, mid_residual=mu)
         record: Dict[str, Tuple[Tensor, Tensor]] = {}
         with torch.enable_grad():
-            eps_c = unet_forward(sd, cfg, control, t, text[[1]], record=record, guidance_blocks=gb)
+            eps_c = unet_forward(sd, cfg, control, t, text[[1]], record=record, guidance_blocks=gb, down_residuals=dc,
+                                 mid_residual=mc_)
             probs = record_to_probs(record, mm_heads)
             raw = motion_loss(probs, representation)
             loss = icfg["motion_guidance_weight"] * raw
@@ -453,18 +552,21 @@ def single_step(sd, cfg, icfg: dict, latents: Tensor, step_index: int, timesteps
         eps = cfg_combine(eps_c.detach(), eps_u, icfg["cfg_scale"])
         return ddim_guided_step(eps, control.detach(), grad.detach(), a_t, a_prev, 1.0, reciprocal_div).detach()
     with torch.no_grad():
-        pair = unet_forward(sd, cfg, latents.expand(2, -1, -1, -1, -1), t, text, guidance_blocks=gb)
+        pair = unet_forward(sd, cfg, latents.expand(2, -1, -1, -1, -1), t, text, guidance_blocks=gb,
+                            down_residuals=dpair, mid_residual=mpair)
         eps = cfg_combine(pair[[1]], pair[[0]], icfg["cfg_scale"])
         return ddim_guided_step(eps, latents, None, a_t, a_prev, 1.0, reciprocal_div).detach()
 
 
 def sample_loop(sd, cfg, icfg: dict, latents: Tensor, text: Tensor, representation, reciprocal_div: bool = False,
-                stats: Optional[dict] = None, max_steps: Optional[int] = None) -> List[Tensor]:
+                stats: Optional[dict] = None, max_steps: Optional[int] = None,
+                controlnet: Optional[dict] = None) -> List[Tensor]:
     """utils/motionclone_functions.py:102-171 (sample_video) from prepared latents to final latents (VAE excluded)."""
     timesteps = uneven_timesteps(icfg["inference_steps"], icfg["guidance_steps"], icfg["guidance_scale"])
     acp = alphas_cumprod()
     per_step = []
     for i in range(len(timesteps) if max_steps is None else max_steps):
-        latents = single_step(sd, cfg, icfg, latents, i, timesteps, acp, text, representation, reciprocal_div, stats)
+        latents = single_step(sd, cfg, icfg, latents, i, timesteps, acp, text, representation, reciprocal_div, stats,
+                              controlnet)
         per_step.append(latents)
     return per_step

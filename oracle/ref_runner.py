@@ -50,14 +50,19 @@ class _LatentDist:
 
 
 class _StubVAE:
-    """vae.encode(video).latent_dist.sample() -> preset clip latents [(f), 4, h, w]; scaling_factor 1 (off path)."""
+    """vae.encode(video).latent_dist.sample() -> preset clip latents [(f), 4, h, w]; scaling_factor 1 (off path).
+    A call whose batch is not the clip length is the SparseCtrl condition-image encode
+    (motionclone_functions.py:125): it returns the preset condition latents [(n_img), 4, h, w]."""
 
-    def __init__(self, clip_latents_fchw, dtype, device):
+    def __init__(self, clip_latents_fchw, dtype, device, cond_latents=None):
         self._z = clip_latents_fchw
+        self._cond = cond_latents
         self.dtype, self.device = dtype, device
         self.config = types.SimpleNamespace(scaling_factor=1.0)
 
     def encode(self, x):
+        if self._cond is not None and x.shape[0] != self._z.shape[0]:
+            return types.SimpleNamespace(latent_dist=_LatentDist(self._cond))
         return types.SimpleNamespace(latent_dist=_LatentDist(self._z))
 
     def decode(self, z):
@@ -65,7 +70,7 @@ class _StubVAE:
 
 
 def build_reference_pipeline(unet_config: dict, infer_cfg: dict, inputs: dict, weight_seed: int = 42,
-                             dtype=torch.float32, device="cpu"):
+                             dtype=torch.float32, device="cpu", controlnet_kwargs: dict | None = None):
     """Returns (pipeline, mf). `infer_cfg` carries the YAML keys of configs/t2v_*.yaml plus video_length/height/width."""
     from motionclone_b200.synthetic import NOISE_SCHEDULER_KWARGS, load_synthetic_weights
 
@@ -75,13 +80,25 @@ def build_reference_pipeline(unet_config: dict, infer_cfg: dict, inputs: dict, w
     load_synthetic_weights(unet, weight_seed)
     unet = unet.to(device=device, dtype=dtype).eval()
 
+    controlnet = None
+    if controlnet_kwargs is not None:  # i2v_video_sample.py:41-59 (random-init SparseCtrl; zero-convs drawn non-zero)
+        import motionclone.models.sparse_controlnet as scn
+        unet.config.num_attention_heads = 8
+        unet.config.projection_class_embeddings_input_dim = None
+        controlnet = scn.SparseControlNetModel.from_unet(unet, controlnet_additional_kwargs=dict(controlnet_kwargs))
+        load_synthetic_weights(controlnet, weight_seed + 1)
+        controlnet = controlnet.to(device=device).eval()  # cond embedding stays fp16 as the reference builds it
+        for p in controlnet.parameters():
+            p.requires_grad = False
     pipeline = object.__new__(pipe_mod.AnimationPipeline)  # skip DiffusionPipeline.register_modules plumbing
     pipeline.unet = unet
-    pipeline.controlnet = None
+    pipeline.controlnet = controlnet
     pipeline.scheduler = DDIMScheduler(**NOISE_SCHEDULER_KWARGS)
     pipeline.vae_scale_factor = 8
     clip = inputs["clip_latents"].to(device=device, dtype=dtype)  # [1,4,f,h,w]
-    pipeline.vae = _StubVAE(clip[0].permute(1, 0, 2, 3).contiguous(), dtype, torch.device(device))
+    cond_lat = inputs.get("cond_latents")  # [n_img, 4, h, w] for the simplified (latent) condition embedding
+    pipeline.vae = _StubVAE(clip[0].permute(1, 0, 2, 3).contiguous(), dtype, torch.device(device),
+                            None if cond_lat is None else cond_lat.to(device=device, dtype=dtype))
     text = inputs["text_embeddings"].to(device=device, dtype=dtype)
     pipeline.tokenizer = lambda *a, **k: types.SimpleNamespace(input_ids=torch.zeros(1, 77, dtype=torch.long))
     pipeline.tokenizer.model_max_length = 77
@@ -110,8 +127,12 @@ def build_reference_pipeline(unet_config: dict, infer_cfg: dict, inputs: dict, w
     pipeline.unet = cl.prep_unet_conv(pipeline.unet)
     pipeline.scheduler.customized_set_timesteps(config.inference_steps, config.guidance_steps, config.guidance_scale,
                                                 device=device, timestep_spacing_type="uneven")
-    # video_preprocess (decord) is off the path: the stub VAE ignores its output
-    mf.video_preprocess = lambda *a, **k: torch.zeros(1)
+    # video_preprocess (decord) is off the path: the stub VAE ignores its output; SparseCtrl's image condition reads the
+    # clip's pixels ([f, 3, H, W] in [-1, 1]) at motionclone_functions.py:51
+    pix = inputs.get("clip_pixels")
+    n_frames = int(infer_cfg["video_length"])
+    mf.video_preprocess = (lambda *a, **k: pix.to(device=device, dtype=dtype)) if pix is not None \
+        else (lambda *a, **k: torch.zeros(n_frames, 3, 8, 8))  # batch == clip length: the stub VAE's "clip" branch
     return pipeline, mf
 
 
@@ -127,19 +148,20 @@ class _NullBar:
 
 
 def run_reference(unet_config: dict, infer_cfg: dict, inputs: dict, repr_path: str, weight_seed: int = 42,
-                  dtype=torch.float32, device="cpu", record_grad_steps=(0,)):
+                  dtype=torch.float32, device="cpu", record_grad_steps=(0,), controlnet_kwargs: dict | None = None):
     """obtain_motion_representation (motionclone_functions.py:25-82) then the sample_video loop (:102-171).
 
     Returns a dict of CPU fp32 tensors: motion representation, per-step latents, per-step losses and the
     guidance gradient at `record_grad_steps`.
     """
-    pipeline, mf = build_reference_pipeline(unet_config, infer_cfg, inputs, weight_seed, dtype, device)
+    pipeline, mf = build_reference_pipeline(unet_config, infer_cfg, inputs, weight_seed, dtype, device, controlnet_kwargs)
+    use_cn = controlnet_kwargs is not None
     out = {}
 
     # --- extraction: randn_tensor(generator) is replaced by the preset clip noise (CUDA/CPU streams differ) ---
     noise = inputs["clip_noise"].to(device=device, dtype=dtype)
     mf.randn_tensor = lambda shape, generator=None, device=None, dtype=None: noise
-    pipeline.obtain_motion_representation(generator=None, motion_representation_path=repr_path)
+    pipeline.obtain_motion_representation(generator=None, motion_representation_path=repr_path, use_controlnet=use_cn)
     rep = torch.load(repr_path)
     probs = pipeline.get_temp_attn_prob()  # processors still hold the extraction pass's q,k
     out["extract_probs_0"] = next(iter(probs.values())).float().cpu()
@@ -184,7 +206,8 @@ def run_reference(unet_config: dict, infer_cfg: dict, inputs: dict, repr_path: s
     pipeline.single_step_video = rec_step
     torch.autograd.grad = rec_grad
     try:
-        pipeline.sample_video(generator=None, noisy_latents=inputs["noisy_latents"].to(device=device, dtype=dtype))
+        pipeline.sample_video(generator=None, noisy_latents=inputs["noisy_latents"].to(device=device, dtype=dtype),
+                              add_controlnet=use_cn)
     finally:
         torch.autograd.grad = ref_autograd_grad
     out["timesteps"] = pipeline.scheduler.timesteps.cpu()

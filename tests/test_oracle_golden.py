@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 import torch
 
-from motionclone_b200.synthetic import UNET_TINY_CONFIG, synthetic_inputs, synthetic_state_dict
+from motionclone_b200.synthetic import (SPARSECTRL_IMAGE_KWARGS, SPARSECTRL_LATENT_KWARGS, UNET_TINY_CONFIG,
+                                        synthetic_condition, synthetic_inputs, synthetic_state_dict)
 from oracle import mc_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -73,3 +74,34 @@ def test_c1_fixture_present_and_consistent():
     assert meta["infer"]["inference_steps"] == 10 and meta["unet"] == "sd15"
     assert list(g["timesteps"]) == list(O.uneven_timesteps(10, 5, 0.3)) == [999, 924, 850, 775, 700, 699, 524, 350, 175, 0]
     assert np.isfinite(g["latents_per_step"]).all()
+
+
+@pytest.mark.parametrize("case", ["tiny8_i2v_latent", "tiny8_i2v_image"])
+def test_sparsectrl_path(case):
+    """SparseControlNetModel.forward + condition assembly, pinned against the reference's own run
+    (random-init SparseCtrl, zero-convs drawn non-zero; latent condition = i2v_rgb, image condition = i2v_sketch).
+    The reference hard-codes the condition embedding to fp16 (sparse_controlnet.py:184,190,523), so fp32 "truth" carries
+    one fp16 convolution: bar 1e-4 relative (observed 5e-7)."""
+    g, meta, sd, icfg, inp = _case(case)
+    kind = icfg["sparsectrl"]
+    cshapes = json.load(open(os.path.join(GOLDEN, f"ref_state_dict_shapes_controlnet_{kind}.json")))
+    sdc = synthetic_state_dict(cshapes, meta["weight_seed"] + 1)
+    sdc = {k: (v.half() if k.startswith("controlnet_cond_embedding") else v) for k, v in sdc.items()}
+    cond = synthetic_condition(kind, len(icfg["image_index"]), icfg["height"], icfg["width"], icfg["video_length"],
+                               meta["input_seed"] + 5)
+    cn = dict(sd=sdc, kwargs=SPARSECTRL_LATENT_KWARGS if kind == "latent" else SPARSECTRL_IMAGE_KWARGS,
+              image_index=icfg["image_index"], scale=icfg["controlnet_scale"])
+    rep, _ = O.obtain_motion_representation(sd, UNET_TINY_CONFIG, inp["clip_latents"], inp["clip_noise"],
+                                            inp["text_embeddings"][[0]], icfg["add_noise_step"], controlnet=cn,
+                                            clip_pixels=cond.get("clip_pixels"))
+    for i, n in enumerate(rep):
+        _close(rep[n][0], g[f"repr_val_{i}"], 1e-4)
+        assert torch.equal(rep[n][1], torch.from_numpy(g[f"repr_idx_{i}"]))
+    images = cond["cond_latents"] if kind == "latent" else cond["cond_images"]
+    cn["images"] = images.permute(1, 0, 2, 3).unsqueeze(0)
+    stats = {}
+    steps = O.sample_loop(sd, UNET_TINY_CONFIG, icfg, inp["noisy_latents"], inp["text_embeddings"], rep, stats=stats,
+                          controlnet=cn, max_steps=3)  # guided, guided, first plain
+    for i, s_ in enumerate(steps):
+        _close(s_, g["latents_per_step"][i], 1e-4)
+    _close(stats["grad"][0], g["grad_step_0"], 1e-4)

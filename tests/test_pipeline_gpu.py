@@ -14,8 +14,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import mc_oracle as O  # noqa: E402
-from motionclone_b200.synthetic import (UNET_SD15_CONFIG, UNET_TINY_CONFIG, synthetic_inputs,  # noqa: E402
-                                        synthetic_state_dict)
+from motionclone_b200.synthetic import (SPARSECTRL_IMAGE_KWARGS, SPARSECTRL_LATENT_KWARGS, UNET_SD15_CONFIG,  # noqa: E402
+                                        UNET_TINY_CONFIG, synthetic_condition, synthetic_inputs, synthetic_state_dict)
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -39,12 +39,34 @@ def _build(case, dev):
     inp = synthetic_inputs(icfg["video_length"], icfg["height"], icfg["width"], ucfg["cross_attention_dim"],
                            meta["input_seed"])
     icfg.update(video_latents=inp["clip_latents"].half(), video_noise=inp["clip_noise"].half(), new_prompt="synthetic")
-    pipe = mc.build_pipeline(ucfg, icfg, device=dev, weight_seed=meta["weight_seed"])
+    cn_kwargs = None
+    if icfg.get("sparsectrl"):  # SparseCtrl cases (BASELINE configs[3], [4] topology): synthetic condition inputs
+        kind = icfg["sparsectrl"]
+        cn_kwargs = SPARSECTRL_LATENT_KWARGS if kind == "latent" else SPARSECTRL_IMAGE_KWARGS
+        cond = synthetic_condition(kind, len(icfg["image_index"]), icfg["height"], icfg["width"], icfg["video_length"],
+                                   meta["input_seed"] + 5)
+        inp.update(cond)
+        images = cond["cond_latents"] if kind == "latent" else cond["cond_images"]
+        inp["controlnet_images"] = images.permute(1, 0, 2, 3).unsqueeze(0)  # [1, c, n_img, h, w]
+        icfg.update(controlnet_images=inp["controlnet_images"].half(), video_pixels=cond.get("clip_pixels"))
+    pipe = mc.build_pipeline(ucfg, icfg, device=dev, weight_seed=meta["weight_seed"], controlnet_kwargs=cn_kwargs)
     pipe.set_prompt_embeds(inp["text_embeddings"].to(dev, torch.float16))
+    inp["cn_kwargs"] = cn_kwargs
     return pipe, g, meta, inp, ucfg
 
 
-@pytest.fixture(scope="module", params=["tiny8", "tiny16", "c1"])
+def _oracle_controlnet(run_or_pipe, meta, inp, dev):
+    """dict for the oracle's controlnet arguments (fp16 on device), or None for the t2v cases."""
+    if inp.get("cn_kwargs") is None:
+        return None
+    pipe = run_or_pipe
+    shapes = {k: v.shape for k, v in pipe.controlnet.state_dict().items()}
+    sdc = {k: v.to(dev, torch.float16) for k, v in synthetic_state_dict(shapes, meta["weight_seed"] + 1).items()}
+    return dict(sd=sdc, kwargs=inp["cn_kwargs"], image_index=meta["infer"]["image_index"],
+                scale=meta["infer"]["controlnet_scale"], images=inp["controlnet_images"].to(dev, torch.float16))
+
+
+@pytest.fixture(scope="module", params=["tiny8", "tiny16", "c1", "tiny8_i2v_latent", "tiny8_i2v_image"])
 def run(request):
     assert torch.cuda.is_available()
     dev = torch.device("cuda:0")
@@ -52,7 +74,8 @@ def run(request):
     with torch.no_grad():
         fwd = pipe.unet(inp["noisy_latents"].to(dev, torch.float16), 500,
                         encoder_hidden_states=inp["text_embeddings"][[1]].to(dev, torch.float16)).sample
-    rep = pipe.obtain_motion_representation(motion_representation_path=None)
+    use_cn = inp.get("cn_kwargs") is not None
+    rep = pipe.obtain_motion_representation(motion_representation_path=None, use_controlnet=use_cn)
     # the sampling loop is compared with the reference on the REFERENCE's motion representation (identical inputs);
     # the package's own extraction is checked separately in test_motion_representation_vs_reference
     pipe.motion_representation_dict = {str(n): [torch.from_numpy(g[f"repr_val_{i}"]).half(),
@@ -70,7 +93,8 @@ def run(request):
         return out
 
     pipe.single_step_video = rec
-    final = pipe.sample_video(noisy_latents=inp["noisy_latents"].to(dev, torch.float16), return_latents=True)
+    final = pipe.sample_video(noisy_latents=inp["noisy_latents"].to(dev, torch.float16), return_latents=True,
+                              add_controlnet=use_cn)
     return dict(case=request.param, pipe=pipe, g=g, meta=meta, inp=inp, ucfg=ucfg, fwd=fwd, rep=rep,
                 per_step=per_step, losses=losses, grads=grads, final=final, dev=dev)
 
@@ -124,7 +148,8 @@ def test_guidance_loss_and_gradient_vs_reference(run):
     rep = {str(n): [h(torch.from_numpy(g[f"repr_val_{i}"])), torch.from_numpy(g[f"repr_idx_{i}"]).to(dev)]
            for i, n in enumerate(g["repr_names"])}
     stats = {}
-    O.sample_loop(sd, ucfg, icfg, h(inp["noisy_latents"]), h(inp["text_embeddings"]), rep, stats=stats, max_steps=1)
+    O.sample_loop(sd, ucfg, icfg, h(inp["noisy_latents"]), h(inp["text_embeddings"]), rep, stats=stats, max_steps=1,
+                  controlnet=_oracle_controlnet(run["pipe"], meta, inp, dev))
     r_eager = _rel(stats["grad"][0], g["grad_step_0"])
     print(run["case"], f"grad step 0: rel max err {r:.4f} (eager fp16 op sequence: {r_eager:.4f}), cosine {cos:.6f}")
     # fp16 backward through ~60 % of the UNet vs fp32 autograd: no worse than 1.5x the eager fp16 path's own error
@@ -149,14 +174,16 @@ def test_latents_vs_same_device_oracle(run):
     sd = {k: v.to(dev, torch.float16) for k, v in synthetic_state_dict(shapes, meta["weight_seed"]).items()}
     icfg = meta["infer"]
     h = lambda t: t.to(dev, torch.float16)  # noqa: E731
+    cn = _oracle_controlnet(run["pipe"], meta, inp, dev)
     rep, _ = O.obtain_motion_representation(sd, ucfg, h(inp["clip_latents"]), h(inp["clip_noise"]),
-                                            h(inp["text_embeddings"][[0]]), icfg["add_noise_step"])
+                                            h(inp["text_embeddings"][[0]]), icfg["add_noise_step"], controlnet=cn,
+                                            clip_pixels=None if inp.get("clip_pixels") is None else h(inp["clip_pixels"]))
     mism = sum(int((rep[n][1] != run["rep"][n][1]).sum()) for n in rep)
     tot = sum(rep[n][1].numel() for n in rep)
     g = run["g"]
     gold = {str(n): [h(torch.from_numpy(g[f"repr_val_{i}"])), torch.from_numpy(g[f"repr_idx_{i}"]).to(dev)]
             for i, n in enumerate(g["repr_names"])}
-    steps = O.sample_loop(sd, ucfg, icfg, h(inp["noisy_latents"]), h(inp["text_embeddings"]), gold)
+    steps = O.sample_loop(sd, ucfg, icfg, h(inp["noisy_latents"]), h(inp["text_embeddings"]), gold, controlnet=cn)
     rels = [_rel(run["per_step"][i], steps[i].cpu()) for i in range(len(steps))]
     print(run["case"], f"vs fp16 oracle on device: index mismatches {mism}/{tot}; per-step latent rel err {rels}")
     assert mism / tot < 0.02
