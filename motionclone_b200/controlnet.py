@@ -182,10 +182,12 @@ class SparseControlNetModel(nn.Module):
 
     def _condition_embedding(self, controlnet_cond, conditioning_mask):
         """[1, c, f, H, W] (+ mask) -> 4-D NHWC fp16 embedding [(f), C0, h, w]; cached: it does not change between steps."""
-        key = (controlnet_cond.data_ptr(), controlnet_cond._version, tuple(controlnet_cond.shape),
-               None if conditioning_mask is None else (conditioning_mask.data_ptr(), conditioning_mask._version))
-        if self._cond_cache is not None and self._cond_cache[0] == key:
-            return self._cond_cache[1]
+        # identity-keyed: the cache holds the tensors, so their storage cannot be recycled under the same address
+        key = (controlnet_cond, conditioning_mask, controlnet_cond._version,
+               None if conditioning_mask is None else conditioning_mask._version)
+        c = self._cond_cache
+        if c is not None and c[0][0] is controlnet_cond and c[0][1] is conditioning_mask and c[0][2:] == key[2:]:
+            return c[1]
         cond = controlnet_cond
         if self.concate_conditioning_mask:
             cond = torch.cat([controlnet_cond, conditioning_mask], dim=1)

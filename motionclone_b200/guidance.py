@@ -78,9 +78,10 @@ def _controlnet_residuals(self, latents, step_t, text, images):
     inside the controlnet."""
     cfg = self.input_config
     idx = list(_cfg_get(cfg, "image_index"))
-    key = (images.data_ptr(), images._version, tuple(images.shape), latents.shape[2], tuple(idx))
+    # identity-keyed (the cache keeps `images` alive, so its storage cannot be recycled under the same address)
+    key = (images, images._version, latents.shape[2], tuple(idx), latents.dtype)
     cache = getattr(self, "_cn_cond_cache", None)
-    if cache is None or cache[0] != key:
+    if cache is None or cache[0][0] is not images or cache[0][1:] != key[1:]:
         shp = list(images.shape)
         shp[2] = latents.shape[2]
         cond = torch.zeros(shp, device=latents.device, dtype=latents.dtype)
