@@ -158,7 +158,8 @@ def run_reference_arm(args):
     fps = fps_from_step_times(tg, tp, infer)
     sample = (f"{info['measured']} at 16x512x512 (fp32 CPU oracle, math attention), extrapolated to "
               f"{infer['inference_steps']} steps ({infer['guidance_steps']} guided)")
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": 0, "steps": args.steps,
+    line = {"impl": "reference", "device": "cpu", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * infer["video_length"] / fps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "t2v_object 16x512x512, 50-step DDIM (30 guided), SD1.5+mm widths, CPU oracle port"},

@@ -110,6 +110,16 @@ int mc_cfg_ddim_step(const void* eps_cond, const void* eps_uncond, const void* x
 int mc_add_noise(const void* x0, const void* noise, void* out, int64_t n, float sqrt_alpha, float sqrt_one_minus_alpha,
                  void* stream);
 
+/*
+ * Text cross-attention forward on tcgen05 tensor cores with TMEM accumulators (csrc/cross_attn_tc.cu):
+ * O = softmax(scale * Q K^T) V per (batch, head), Q [B, Nq, H*DH] (all frames of one prompt), K, V [B, Nk <= 80, H*DH].
+ * Replaces the xformers call for `attn2` (models/attention.py:193-201, :280-285 -> :535-542) in the inference passes.
+ * Strides in elements (multiples of 8); head h occupies columns [h*DH, (h+1)*DH). DH in {16, 32, 40, 64, 80, 160}.
+ */
+int mc_cross_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int Nq, int Nk, int H, int DH,
+                      int64_t q_stride_b, int64_t q_stride_row, int64_t kv_stride_b, int64_t kv_stride_row,
+                      int64_t o_stride_b, int64_t o_stride_row, float scale, void* stream);
+
 /* out = a + bias[c] + b on channel-innermost fp16 tensors (n elements, C channels): the resnet's residual add
  * `input_tensor + hidden_states` (models/resnet.py:209-211) with conv2's (+ the shortcut conv's) bias folded in. */
 int mc_bias_residual_add(const void* a, const void* b, const void* bias, void* out, int64_t n, int C, void* stream);

@@ -262,6 +262,102 @@ __device__ __forceinline__ int64_t out_row(int b, int p_first, int p_last, int h
 // ================================================================================================================
 // forward
 // ================================================================================================================
+// One (position[-pair], head) item of the forward: scores, softmax, per-row by-products, O = P V over the item's Q rows.
+// `bar_v` (nullable): barrier of a separately staged V, waited on first use.
+template <typename C>
+__device__ __forceinline__ void fwd_item(const TAParams& prm, const TileGeom& g, uint8_t* sQ, uint32_t sQa, uint32_t sKa,
+                                         uint32_t sVa, int b, int p0, int h0, int item, int lane, bool has_o,
+                                         uint64_t* bar_v, bool& v_ready) {
+  constexpr int DH = C::DH;
+  constexpr int L = C::L;
+  const int gq = lane >> 2, t = lane & 3;
+  const int pl0 = (item / g.HG) * C::PP;
+  const int hl = item % g.HG;
+  const int colbase = hl * DH;
+  const int h = h0 + hl;
+#pragma unroll
+  for (int mt = 0; mt < C::MT; ++mt) {
+    float s[C::NKT][4];
+    qk_scores<C>(s, sQa, sKa, mt, pl0, colbase, g, lane);
+    softmax_rows<C>(s, prm.scale);
+
+    // ---- per-row outputs: probabilities, top-1 (lowest index on ties), gathered probability ----
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int64_t R = out_row<C>(b, p0 + pl0, p0 + g.P - 1, h, mt, gq, hf, prm.D, prm.H);
+      if (prm.probs != nullptr) {
+        __half* prow = prm.probs + R * L;
+#pragma unroll
+        for (int nt = 0; nt < C::NKT; ++nt) {
+          if (L == 8 && nt != hf) continue;
+          const int col = (L == 8 ? 0 : nt * 8) + 2 * t;
+          *reinterpret_cast<__half2*>(prow + col) = __floats2half2_rn(s[nt][2 * hf], s[nt][2 * hf + 1]);
+        }
+      }
+      if (prm.top_val != nullptr) {
+        float bv = -1.f;
+        int bi = 0;
+#pragma unroll
+        for (int nt = 0; nt < C::NKT; ++nt) {
+          if (L == 8 && nt != hf) continue;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float pv = s[nt][2 * hf + e];
+            const int col = (L == 8 ? 0 : nt * 8) + 2 * t + e;
+            if (pv > bv) {
+              bv = pv;
+              bi = col;
+            }
+          }
+        }
+#pragma unroll
+        for (int off = 1; off <= 2; off <<= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+          if (ov > bv || (ov == bv && oi < bi)) {
+            bv = ov;
+            bi = oi;
+          }
+        }
+        if (t == 0) {
+          prm.top_val[R] = __float2half_rn(bv);
+          prm.top_idx[R] = (uint8_t)bi;
+        }
+      }
+      if (prm.gathered != nullptr) {
+        const int gi = prm.gather_idx[R];
+#pragma unroll
+        for (int nt = 0; nt < C::NKT; ++nt) {
+          if (L == 8 && nt != hf) continue;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = (L == 8 ? 0 : nt * 8) + 2 * t + e;
+            if (col == gi) prm.gathered[R] = __float2half_rn(s[nt][2 * hf + e]);
+          }
+        }
+      }
+    }
+
+    // ---- O = P V, written over this item's Q rows ----
+    if (has_o) {
+      if (!v_ready) {
+        if (bar_v != nullptr) mbar_wait(bar_v, 0);
+        v_ready = true;
+      }
+      uint32_t pa[C::KK][4];
+      probs_to_afrag<C>(pa, s);
+      float acc[C::NDT][4];
+#pragma unroll
+      for (int nd = 0; nd < C::NDT; ++nd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
+      mma_a_rowmajor_b<C>(acc, pa, sVa, pl0, colbase, g, lane);
+      __syncwarp();  // every lane's ldmatrix of this tile's Q rows has completed before they are overwritten
+      store_acc<C>(acc, 1.f, sQ, mt, pl0, colbase, g, lane);
+    }
+  }
+}
+
 template <int DH, int L, int NW>
 __global__ void __launch_bounds__(NW * 32) temporal_attn_fwd_kernel(const TAParams prm) {
   using C = TACfg<DH, L>;
@@ -311,96 +407,10 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_fwd_kernel(const TAPara
 
   const int n_items = ((g.P + C::PP - 1) / C::PP) * g.HG;
   const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(sV);
-  const int gq = lane >> 2, t = lane & 3;
   bool v_ready = false;
 
-  for (int item = warp; item < n_items; item += NW) {
-    const int pl0 = (item / g.HG) * C::PP;
-    const int hl = item % g.HG;
-    const int colbase = hl * DH;
-    const int h = h0 + hl;
-#pragma unroll
-    for (int mt = 0; mt < C::MT; ++mt) {
-      float s[C::NKT][4];
-      qk_scores<C>(s, sQa, sKa, mt, pl0, colbase, g, lane);
-      softmax_rows<C>(s, prm.scale);
-
-      // ---- per-row outputs: probabilities, top-1 (lowest index on ties), gathered probability ----
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const int64_t R = out_row<C>(b, p0 + pl0, p0 + g.P - 1, h, mt, gq, hf, prm.D, prm.H);
-        if (prm.probs != nullptr) {
-          __half* prow = prm.probs + R * L;
-#pragma unroll
-          for (int nt = 0; nt < C::NKT; ++nt) {
-            if (L == 8 && nt != hf) continue;
-            const int col = (L == 8 ? 0 : nt * 8) + 2 * t;
-            *reinterpret_cast<__half2*>(prow + col) = __floats2half2_rn(s[nt][2 * hf], s[nt][2 * hf + 1]);
-          }
-        }
-        if (prm.top_val != nullptr) {
-          float bv = -1.f;
-          int bi = 0;
-#pragma unroll
-          for (int nt = 0; nt < C::NKT; ++nt) {
-            if (L == 8 && nt != hf) continue;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float pv = s[nt][2 * hf + e];
-              const int col = (L == 8 ? 0 : nt * 8) + 2 * t + e;
-              if (pv > bv) {
-                bv = pv;
-                bi = col;
-              }
-            }
-          }
-#pragma unroll
-          for (int off = 1; off <= 2; off <<= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (ov > bv || (ov == bv && oi < bi)) {
-              bv = ov;
-              bi = oi;
-            }
-          }
-          if (t == 0) {
-            prm.top_val[R] = __float2half_rn(bv);
-            prm.top_idx[R] = (uint8_t)bi;
-          }
-        }
-        if (prm.gathered != nullptr) {
-          const int gi = prm.gather_idx[R];
-#pragma unroll
-          for (int nt = 0; nt < C::NKT; ++nt) {
-            if (L == 8 && nt != hf) continue;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int col = (L == 8 ? 0 : nt * 8) + 2 * t + e;
-              if (col == gi) prm.gathered[R] = __float2half_rn(s[nt][2 * hf + e]);
-            }
-          }
-        }
-      }
-
-      // ---- O = P V, written over this item's Q rows ----
-      if (has_o) {
-        if (!v_ready) {
-          if (!g.fused) mbar_wait(bar_v, 0);
-          v_ready = true;
-        }
-        uint32_t pa[C::KK][4];
-        probs_to_afrag<C>(pa, s);
-        float acc[C::NDT][4];
-#pragma unroll
-        for (int nd = 0; nd < C::NDT; ++nd)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
-        mma_a_rowmajor_b<C>(acc, pa, sVa, pl0, colbase, g, lane);
-        __syncwarp();  // every lane's ldmatrix of this tile's Q rows has completed before they are overwritten
-        store_acc<C>(acc, 1.f, sQ, mt, pl0, colbase, g, lane);
-      }
-    }
-  }
+  for (int item = warp; item < n_items; item += NW)
+    fwd_item<C>(prm, g, sQ, sQa, sKa, sVa, b, p0, h0, item, lane, has_o, g.fused ? nullptr : bar_v, v_ready);
 
   if (has_o) {
     fence_proxy_async();
@@ -410,6 +420,115 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_fwd_kernel(const TAPara
       store_rows<L>(prm.o, sQ, g.pitch, g.PS, g.W, g.P, prm.out, obase, lane);
       bulk_commit();
       bulk_wait_read_all();
+    }
+  }
+}
+
+// ================================================================================================================
+// forward, persistent + pipelined: one CTA per SM slot loops over tiles. Warp 0 is the producer (bulk loads of tile
+// i+1.. into a ring of NSTAGE shared-memory stages, bulk stores of finished O tiles), warps 1..NCW consume.
+//   full[s]  : producer arrive.expect_tx + TMA complete_tx  -> consumers
+//   empty[s] : one arrive per consumer warp (after its O rows are in shared memory) -> producer
+// Loads of the next tiles are in flight while the current one is computed, and there is no wave quantisation: the
+// non-persistent kernel above loses both at the small layers (profiles/README.md).
+// ================================================================================================================
+template <int DH, int L, int NCW, int NSTAGE>
+__global__ void __launch_bounds__((NCW + 1) * 32) temporal_attn_fwd_persistent_kernel(const TAParams prm, int n_tiles) {
+  using C = TACfg<DH, L>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + NSTAGE;
+  const TileGeom g = prm.g;
+  const int stage_bytes = (g.fused ? 1 : 3) * g.tensor_bytes;
+  uint8_t* stage0 = smem + kHeaderBytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_hg = prm.H / g.HG, n_pt = prm.D / g.P;
+  const bool has_o = prm.o != nullptr;
+  const uint32_t tbytes = (uint32_t)L * g.P * g.W * 2;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, NCW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto coords = [&](int tile, int& b, int& p0, int& h0) {
+    const int hg = tile % n_hg;
+    const int t2 = tile / n_hg;
+    b = t2 / n_pt;
+    p0 = (t2 % n_pt) * g.P;
+    h0 = hg * g.HG;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------ producer ------------------------------------------------
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int s = it % NSTAGE, r = it / NSTAGE;
+      uint8_t* sQ = stage0 + s * stage_bytes;
+      int b, p0, h0;
+      if (r > 0) {  // the tile that used this stage NSTAGE iterations ago: wait for its consumers, send its O home
+        mbar_wait(empty + s, (r - 1) & 1);
+        if (has_o) {
+          coords(tile - NSTAGE * (int)gridDim.x, b, p0, h0);
+          const int64_t obase = (int64_t)b * prm.out.stride_b + (int64_t)p0 * prm.out.stride_p + h0 * DH;
+          store_rows<L>(prm.o, sQ, g.pitch, g.PS, g.W, g.P, prm.out, obase, lane);
+          bulk_commit();
+          bulk_wait_read_all();  // the stage may be overwritten once the store engine has read it
+        }
+        __syncwarp();
+      }
+      coords(tile, b, p0, h0);
+      const int64_t gbase = (int64_t)b * prm.in.stride_b + (int64_t)p0 * prm.in.stride_p + h0 * DH;
+      if (g.fused) {
+        if (lane == 0) mbar_arrive_expect_tx(full + s, 3 * tbytes);
+        __syncwarp();
+        stage_rows<L>(sQ, g.pitch, g.PS, 3 * g.W, g.P, prm.q, prm.in, gbase, full + s, lane);
+      } else {
+        if (lane == 0) mbar_arrive_expect_tx(full + s, (has_o ? 3 : 2) * tbytes);
+        __syncwarp();
+        stage_rows<L>(sQ, g.pitch, g.PS, g.W, g.P, prm.q, prm.in, gbase, full + s, lane);
+        stage_rows<L>(sQ + g.tensor_bytes, g.pitch, g.PS, g.W, g.P, prm.k, prm.in, gbase, full + s, lane);
+        if (has_o) stage_rows<L>(sQ + 2 * g.tensor_bytes, g.pitch, g.PS, g.W, g.P, prm.v, prm.in, gbase, full + s, lane);
+      }
+    }
+    // drain: O of the last (up to NSTAGE) tiles
+    const int n_it = it;
+    for (int j = (n_it > NSTAGE ? n_it - NSTAGE : 0); j < n_it; ++j) {
+      const int s = j % NSTAGE, r = j / NSTAGE;
+      mbar_wait(empty + s, r & 1);
+      if (has_o) {
+        int b, p0, h0;
+        coords(blockIdx.x + j * (int)gridDim.x, b, p0, h0);
+        const int64_t obase = (int64_t)b * prm.out.stride_b + (int64_t)p0 * prm.out.stride_p + h0 * DH;
+        store_rows<L>(prm.o, stage0 + s * stage_bytes, g.pitch, g.PS, g.W, g.P, prm.out, obase, lane);
+        bulk_commit();
+      }
+    }
+    bulk_wait_read_all();
+  } else {
+    // ------------------------------------------------ consumers -----------------------------------------------
+    const int cw = warp - 1;
+    const int n_items = ((g.P + C::PP - 1) / C::PP) * g.HG;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int s = it % NSTAGE, r = it / NSTAGE;
+      uint8_t* sQ = stage0 + s * stage_bytes;
+      uint8_t* sK = g.fused ? sQ + g.W * 2 : sQ + g.tensor_bytes;
+      uint8_t* sV = g.fused ? sQ + g.W * 4 : sQ + 2 * g.tensor_bytes;
+      int b, p0, h0;
+      coords(tile, b, p0, h0);
+      mbar_wait(full + s, r & 1);
+      bool v_ready = true;
+      for (int item = cw; item < n_items; item += NCW)
+        fwd_item<C>(prm, g, sQ, smem_u32(sQ), smem_u32(sK), smem_u32(sV), b, p0, h0, item, lane, has_o, nullptr, v_ready);
+      if (has_o) fence_proxy_async();  // O rows (generic-proxy writes) -> visible to the bulk-store engine
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
     }
   }
 }
@@ -688,12 +807,39 @@ static bool layout_ok(const mc_temporal_layout& l) {
   return l.stride_b % 8 == 0 && l.stride_f % 8 == 0 && l.stride_p % 8 == 0;
 }
 
+template <int DH, int L, int NCW>
+static int launch_fwd_persistent(TAParams& prm, int n_tiles, cudaStream_t st) {
+  constexpr int NSTAGE = 3;
+  const int stage = (prm.g.fused ? 1 : 3) * prm.g.tensor_bytes;
+  const int smem = kHeaderBytes + NSTAGE * stage;
+  if (smem > 227 * 1024) return 1;  // caller falls back to the one-tile-per-CTA kernel
+  int per_sm = (227 * 1024) / (smem + 1024);
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int grid = per_sm * 148;
+  if (grid > n_tiles) grid = n_tiles;
+  auto kern = temporal_attn_fwd_persistent_kernel<DH, L, NCW, NSTAGE>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  kern<<<grid, (NCW + 1) * 32, smem, st>>>(prm, n_tiles);
+  count_launch();
+  return check_launch("temporal_attn_fwd(persistent)");
+}
+
 template <int DH, int L>
 static int launch_fwd(TAParams& prm, cudaStream_t st) {
   choose_geom(prm.D, L, prm.H, DH, 3, L == 8, is_fusable(prm, prm.H * DH) && prm.o != nullptr, &prm.g);
   const int smem = tile_smem(prm.g, 3);
   const int64_t grid = (int64_t)prm.B * (prm.D / prm.g.P) * (prm.H / prm.g.HG);
   const int n_items = ((prm.g.P + TACfg<DH, L>::PP - 1) / TACfg<DH, L>::PP) * prm.g.HG;
+  // The persistent / pipelined variant is kept as a measured experiment (profiles/README.md): on B200 it is not faster
+  // than 6-7 independent 30 KB CTAs per SM, because the kernel is bound by per-item instruction latency as much as by
+  // bytes in flight, and two 9-warp CTAs per SM give fewer resident warps. Opt in with MC_PERSISTENT=1.
+  static const int env_persist = getenv("MC_PERSISTENT") ? atoi(getenv("MC_PERSISTENT")) : 0;
+  if (env_persist) {
+    const int rc = (n_items >= 8) ? launch_fwd_persistent<DH, L, 8>(prm, (int)grid, st)
+                                  : launch_fwd_persistent<DH, L, 4>(prm, (int)grid, st);
+    if (rc <= 0) return rc;
+  }
   static const int env_nw = getenv("MC_WARPS") ? atoi(getenv("MC_WARPS")) : 0;  // tuning knob
   if (env_nw ? env_nw == 8 : n_items >= 16) {
     auto kern = temporal_attn_fwd_kernel<DH, L, 8>;

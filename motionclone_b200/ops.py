@@ -485,3 +485,20 @@ class BiasResidualAddFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return g, g, None
+
+
+def cross_attention_forward(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float) -> Tensor:
+    """tcgen05 text cross-attention (csrc/cross_attn_tc.cu): q [B, Nq, C], k / v [B, Nk <= 80, C] -> [B, Nq, C]."""
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        _require(t, name)
+        if t.dim() != 3 or t.stride(2) != 1:
+            raise ValueError(f"{name} must be [B, N, C] with contiguous channels")
+    if k.shape != v.shape or k.stride() != v.stride():
+        raise ValueError("k and v must share shape and strides")
+    B, Nq, C = q.shape
+    o = torch.empty((B, Nq, C), dtype=q.dtype, device=q.device)
+    st = _lib.lib().mc_cross_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), B, Nq, k.shape[1], heads, C // heads,
+                                      q.stride(0), q.stride(1), k.stride(0), k.stride(1), o.stride(0), o.stride(1),
+                                      float(scale), _stream())
+    _lib.check(st, "mc_cross_attn_fwd")
+    return o

@@ -410,3 +410,29 @@ def test_bias_residual_add():
     bg = b.clone().requires_grad_(True)
     ga, gb = torch.autograd.grad(ops.BiasResidualAddFn.apply(ag, bg, bias).float().sum(), (ag, bg))
     assert torch.equal(ga, torch.ones_like(a)) and torch.equal(gb, torch.ones_like(b))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# S2: text cross-attention on tcgen05 / TMEM
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,Nq,Nk,H,DH", [(1, 256, 77, 8, 40), (2, 1024, 77, 8, 80), (1, 384, 77, 8, 160), (1, 128, 77, 2, 16),
+                                          (1, 200, 77, 8, 32), (1, 4096, 77, 8, 40), (1, 128, 64, 8, 64)])
+def test_cross_attention_tcgen05(B, Nq, Nk, H, DH):
+    """reference: CrossAttention attn2 through xformers.ops.memory_efficient_attention (models/attention.py:535-542):
+    softmax(q k^T * dh^-0.5) v, fp32 softmax statistics, one rounding of the output."""
+    ops, dev = _ops(), _dev()
+    C = H * DH
+    g = torch.Generator().manual_seed(Nq + DH)
+    q = torch.randn(B, Nq, C, generator=g).to(dev, torch.float16)
+    kv = torch.randn(B, Nk, 2 * C, generator=g).to(dev, torch.float16)
+    k, v = kv[..., :C], kv[..., C:]  # strided rows (a fused K|V projection)
+    scale = DH ** -0.5
+    o = ops.cross_attention_forward(q, k, v, H, scale)
+    qh, kh, vh = (t.float().reshape(B, -1, H, DH).transpose(1, 2) for t in (q, k, v))
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1) @ vh).transpose(1, 2).reshape(B, Nq, C)
+    lib = torch.nn.functional.scaled_dot_product_attention(
+        *(t.reshape(B, -1, H, DH).transpose(1, 2) for t in (q, k.contiguous(), v.contiguous())), scale=scale
+    ).transpose(1, 2).reshape(B, Nq, C)
+    err, err_lib = (o.float() - ref).abs().max().item(), (lib.float() - ref).abs().max().item()
+    # P is rounded to fp16 before PV (as flash kernels do) and O once: a few fp16 ulps of O(1) values
+    assert err <= max(3e-3, 2.0 * err_lib), (err, err_lib)
