@@ -113,12 +113,24 @@ int mc_add_noise(const void* x0, const void* noise, void* out, int64_t n, float 
 /*
  * Text cross-attention forward on tcgen05 tensor cores with TMEM accumulators (csrc/cross_attn_tc.cu):
  * O = softmax(scale * Q K^T) V per (batch, head), Q [B, Nq, H*DH] (all frames of one prompt), K, V [B, Nk <= 80, H*DH].
- * Replaces the xformers call for `attn2` (models/attention.py:193-201, :280-285 -> :535-542) in the inference passes.
+ * Replaces the xformers call for `attn2` (models/attention.py:193-201, :280-285 -> :535-542).
  * Strides in elements (multiples of 8); head h occupies columns [h*DH, (h+1)*DH). DH in {16, 32, 40, 64, 80, 160}.
  */
 int mc_cross_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int Nq, int Nk, int H, int DH,
                       int64_t q_stride_b, int64_t q_stride_row, int64_t kv_stride_b, int64_t kv_stride_row,
                       int64_t o_stride_b, int64_t o_stride_row, float scale, void* stream);
+
+/*
+ * Gradient of the same cross-attention with respect to Q only (tcgen05, csrc/cross_attn_tc.cu):
+ * dQ = scale * [P o (dO V^T - rowsum(P o dO V^T))] K with P recomputed from Q, K. The text K / V are projections of a
+ * constant prompt embedding through frozen weights (t2v_video_sample.py:67-68), so torch.autograd.grad w.r.t. the
+ * latents (utils/motionclone_functions.py:236) never asks for dK / dV; the Python wrapper raises if it is asked to.
+ * Same shape / stride rules as mc_cross_attn_fwd; d_o and dq are [B, Nq, H*DH] with their own strides.
+ */
+int mc_cross_attn_bwd_dq(const void* q, const void* k, const void* v, const void* d_o, void* dq, int B, int Nq, int Nk,
+                         int H, int DH, int64_t q_stride_b, int64_t q_stride_row, int64_t kv_stride_b,
+                         int64_t kv_stride_row, int64_t do_stride_b, int64_t do_stride_row, int64_t dq_stride_b,
+                         int64_t dq_stride_row, float scale, void* stream);
 
 /* out = a + bias[c] + b on channel-innermost fp16 tensors (n elements, C channels): the resnet's residual add
  * `input_tensor + hidden_states` (models/resnet.py:209-211) with conv2's (+ the shortcut conv's) bias folded in. */

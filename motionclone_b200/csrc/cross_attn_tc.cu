@@ -71,36 +71,99 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 
 struct XAParams {
   const __half *q, *k, *v;
-  __half* o;
-  int64_t q_sb, q_sr, kv_sb, kv_sr, o_sb, o_sr;  // batch / row strides in elements (head h at column h*DH)
+  const __half* d_o;  // bwd only
+  __half* o;          // fwd: O; bwd: dQ
+  int64_t q_sb, q_sr, kv_sb, kv_sr, o_sb, o_sr, do_sb, do_sr;  // batch / row strides in elements (head h at column h*DH)
   int B, Nq, Nk, H;
   float scale;
 };
 
+// Stage `nrows` rows (first global row `row0`, rows >= nvalid are zero-filled) of head-columns [0, DH) of a row-major
+// global tensor into the K-major / MN-major no-swizzle chunk layout: 16-byte chunk (row r, chunk c) at (c*R + r)*16.
+// Consecutive threads read consecutive 16-byte chunks of a row (coalesced); chunks >= DH/8 (the K padding) are zeros.
+template <int DH, int KCQ, int R>
+__device__ __forceinline__ void stage_chunks(uint8_t* sdst, const __half* gsrc, int64_t row_stride, int row0, int nvalid,
+                                             int nrows, int tid) {
+  constexpr int KC = DH / 8;  // real chunks per row
+  for (int i = tid; i < nrows * KC; i += kXThreads) {
+    const int r = i / KC, c = i % KC;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (row0 + r < nvalid) val = *reinterpret_cast<const uint4*>(gsrc + (int64_t)(row0 + r) * row_stride + c * 8);
+    *reinterpret_cast<uint4*>(sdst + (c * R + r) * 16) = val;
+  }
+  if (KCQ > KC) {  // zero the padding chunk(s)
+    for (int i = tid; i < nrows * (KCQ - KC); i += kXThreads) {
+      const int r = i % nrows, c = KC + i / nrows;
+      *reinterpret_cast<uint4*>(sdst + (c * R + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+// softmax(scale * S) of TMEM lane `lane_addr` over the first nk of 80 columns; result as 40 packed half2 (fp16-rounded
+// probabilities, zeros beyond nk). Same arithmetic in the forward and in the backward's recompute.
+__device__ __forceinline__ void softmax_row_tmem(uint32_t lane_addr, int nk, float scale, uint32_t (&ph)[kXN / 2]) {
+  float s[kXN];
+#pragma unroll
+  for (int c = 0; c < kXN / 16; ++c) {
+    uint32_t r[16];
+    tmem_ld16(lane_addr + c * 16, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s[c * 16 + j] = __uint_as_float(r[j]) * scale;
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kXN; ++j)
+    if (j < nk) mx = fmaxf(mx, s[j]);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kXN; ++j) {
+    s[j] = (j < nk) ? __expf(s[j] - mx) : 0.f;
+    sum += s[j];
+  }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int j = 0; j < kXN / 2; ++j) ph[j] = pack_half2(s[2 * j] * inv, s[2 * j + 1] * inv);
+}
+
 template <int DH>
-__global__ void __launch_bounds__(kXThreads, 1) cross_attn_fwd_tc_kernel(const XAParams prm) {
-  constexpr int DHP = (DH + 15) / 16 * 16;  // head dim padded to the MMA K / N granularity
-  constexpr int KCQ = DHP / 8;              // 16-byte chunks per Q / K row
-  constexpr int KS1 = DHP / 16;             // k16 steps of S = Q K^T
-  constexpr int KS2 = kXN / 16;             // k16 steps of O = P V  (80 / 16 = 5)
-  constexpr int TCOLS = 256;                // TMEM columns: S at [0, 80), O at [96, 96 + DHP)
-  constexpr int O_COL = 96;
-  static_assert(O_COL + DHP <= TCOLS, "TMEM budget");
+struct XACfg {
+  static constexpr int DHP = (DH + 15) / 16 * 16;  // head dim padded to the MMA K / N granularity
+  static constexpr int KCQ = DHP / 8;              // 16-byte chunks per Q / K / V / dO row
+  static constexpr int KS1 = DHP / 16;             // k16 steps over the head dim
+  static constexpr int KS2 = kXN / 16;             // k16 steps over the keys (80 / 16 = 5)
+  static constexpr int Q_BYTES = KCQ * kXM * 16;
+  static constexpr int KV_BYTES = KCQ * kXN * 16;
+  static constexpr int P_BYTES = (kXN / 8) * kXM * 16;
+  // forward: O [0, DHP) re-uses the columns of S [0, 80) once every thread holds its probabilities in registers
+  static constexpr int TCOLS_FWD = (DHP <= 128) ? 128 : 256;
+  static constexpr int SMEM_FWD = 128 + Q_BYTES + 2 * KV_BYTES + P_BYTES;
+  // backward: S [0, 80), dP [96, 176); dQ [0, DHP) re-uses both once dS is in shared memory
+  static constexpr int DP_COL = 96;
+  static constexpr int TCOLS_BWD = 256;
+  static constexpr int SMEM_BWD = 128 + 2 * Q_BYTES + 2 * KV_BYTES + P_BYTES;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(kXThreads) cross_attn_fwd_tc_kernel(const XAParams prm) {
+  using X = XACfg<DH>;
+  constexpr int DHP = X::DHP, KCQ = X::KCQ;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);          // MMA-done barrier
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
   uint8_t* sQ = smem + 128;                                   // K-major [KCQ][128][16 B]
-  uint8_t* sK = sQ + KCQ * kXM * 16;                          // K-major [KCQ][80][16 B]
-  uint8_t* sV = sK + KCQ * kXN * 16;                          // MN-major [KCQ][80][16 B] (n-chunk c, key j)
-  uint8_t* sP = sV + KCQ * kXN * 16;                          // K-major [10][128][16 B]
+  uint8_t* sK = sQ + X::Q_BYTES;                              // K-major [KCQ][80][16 B]
+  uint8_t* sV = sK + X::KV_BYTES;                             // MN-major [KCQ][80][16 B] (n-chunk c, key j)
+  uint8_t* sP = sV + X::KV_BYTES;                             // K-major [10][128][16 B]
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.x, qt = blockIdx.y, b = blockIdx.z;  // heads fastest: the 8 CTAs sharing Q rows run together
   const int q0 = qt * kXM;
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TCOLS)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(X::TCOLS_FWD)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -109,31 +172,9 @@ __global__ void __launch_bounds__(kXThreads, 1) cross_attn_fwd_tc_kernel(const X
     fence_mbar_init();
   }
 
-  // ---- stage Q (row = this thread's query), K and V (rows < 80 by the first 80 threads) as 16-byte chunks ----
-  {
-    const int row = q0 + tid;
-    const __half* qrow = prm.q + (int64_t)b * prm.q_sb + (int64_t)row * prm.q_sr + h * DH;
-#pragma unroll
-    for (int c = 0; c < KCQ; ++c) {
-      uint4 val = make_uint4(0u, 0u, 0u, 0u);
-      if (row < prm.Nq && c * 8 < DH) val = *reinterpret_cast<const uint4*>(qrow + c * 8);
-      *reinterpret_cast<uint4*>(sQ + (c * kXM + tid) * 16) = val;
-    }
-    if (tid < kXN) {
-      const __half* krow = prm.k + (int64_t)b * prm.kv_sb + (int64_t)tid * prm.kv_sr + h * DH;
-      const __half* vrow = prm.v + (int64_t)b * prm.kv_sb + (int64_t)tid * prm.kv_sr + h * DH;
-#pragma unroll
-      for (int c = 0; c < KCQ; ++c) {
-        uint4 kk = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
-        if (tid < prm.Nk && c * 8 < DH) {
-          kk = *reinterpret_cast<const uint4*>(krow + c * 8);
-          vv = *reinterpret_cast<const uint4*>(vrow + c * 8);
-        }
-        *reinterpret_cast<uint4*>(sK + (c * kXN + tid) * 16) = kk;
-        *reinterpret_cast<uint4*>(sV + (c * kXN + tid) * 16) = vv;
-      }
-    }
-  }
+  stage_chunks<DH, KCQ, kXM>(sQ, prm.q + (int64_t)b * prm.q_sb + h * DH, prm.q_sr, q0, prm.Nq, kXM, tid);
+  stage_chunks<DH, KCQ, kXN>(sK, prm.k + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, kXN, tid);
+  stage_chunks<DH, KCQ, kXN>(sV, prm.v + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, kXN, tid);
   fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
   tc_fence_before();
   __syncthreads();
@@ -144,7 +185,7 @@ __global__ void __launch_bounds__(kXThreads, 1) cross_attn_fwd_tc_kernel(const X
   if (tid == 0) {
     const uint32_t idesc = umma_instr_desc_f16(kXM, kXN, false);
 #pragma unroll
-    for (int ks = 0; ks < KS1; ++ks) {
+    for (int ks = 0; ks < X::KS1; ++ks) {
       const uint64_t a = umma_smem_desc(smem_u32(sQ) + ks * 2 * kXM * 16, kXM * 16, 128);
       const uint64_t bd = umma_smem_desc(smem_u32(sK) + ks * 2 * kXN * 16, kXN * 16, 128);
       umma_f16(tmem_base, a, bd, idesc, ks > 0 ? 1u : 0u);
@@ -154,52 +195,28 @@ __global__ void __launch_bounds__(kXThreads, 1) cross_attn_fwd_tc_kernel(const X
   mbar_wait(bar, 0);
   tc_fence_after();
 
-  // ---- softmax over the 77 valid keys of row `tid` (TMEM lane tid), P -> fp16 -> sP (K-major chunks) ----
+  // ---- softmax over the valid keys of row `tid` (TMEM lane tid), P -> fp16 -> sP (K-major chunks) ----
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
   {
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float s[kXN];
+    uint32_t ph[kXN / 2];
+    softmax_row_tmem(lane_addr, prm.Nk, prm.scale, ph);
 #pragma unroll
-    for (int c = 0; c < kXN / 16; ++c) {
-      uint32_t r[16];
-      tmem_ld16(lane_addr + c * 16, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) s[c * 16 + j] = __uint_as_float(r[j]) * prm.scale;
-    }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < kXN; ++j)
-      if (j < prm.Nk) mx = fmaxf(mx, s[j]);
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < kXN; ++j) {
-      s[j] = (j < prm.Nk) ? __expf(s[j] - mx) : 0.f;
-      sum += s[j];
-    }
-    const float inv = 1.f / sum;
-#pragma unroll
-    for (int c = 0; c < kXN / 8; ++c) {
-      uint4 pk;
-      pk.x = pack_half2(s[c * 8 + 0] * inv, s[c * 8 + 1] * inv);
-      pk.y = pack_half2(s[c * 8 + 2] * inv, s[c * 8 + 3] * inv);
-      pk.z = pack_half2(s[c * 8 + 4] * inv, s[c * 8 + 5] * inv);
-      pk.w = pack_half2(s[c * 8 + 6] * inv, s[c * 8 + 7] * inv);
-      *reinterpret_cast<uint4*>(sP + (c * kXM + tid) * 16) = pk;
-    }
+    for (int c = 0; c < kXN / 8; ++c)
+      *reinterpret_cast<uint4*>(sP + (c * kXM + tid) * 16) = make_uint4(ph[4 * c], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
   }
   fence_proxy_async();
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();  // every thread's tcgen05.ld of S has completed: its columns may be overwritten by O
   tc_fence_after();
 
   // ---- O = P V  (A = P K-major; B = V MN-major: n-chunks SBO apart, 8-key groups LBO = 128 B apart) ----
   if (tid == 0) {
     const uint32_t idesc = umma_instr_desc_f16(kXM, DHP, true);
 #pragma unroll
-    for (int ks = 0; ks < KS2; ++ks) {
+    for (int ks = 0; ks < X::KS2; ++ks) {
       const uint64_t a = umma_smem_desc(smem_u32(sP) + ks * 2 * kXM * 16, kXM * 16, 128);
       const uint64_t bd = umma_smem_desc(smem_u32(sV) + ks * 2 * 128, 128, kXN * 16);
-      umma_f16(tmem_base + O_COL, a, bd, idesc, ks > 0 ? 1u : 0u);
+      umma_f16(tmem_base, a, bd, idesc, ks > 0 ? 1u : 0u);
     }
     umma_commit(bar);
   }
@@ -208,7 +225,6 @@ __global__ void __launch_bounds__(kXThreads, 1) cross_attn_fwd_tc_kernel(const X
 
   // ---- epilogue: O row `tid` from TMEM -> fp16 -> global ----
   {
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + O_COL;
     const int row = q0 + tid;
     __half* orow = prm.o + (int64_t)b * prm.o_sb + (int64_t)row * prm.o_sr + h * DH;
 #pragma unroll
@@ -234,53 +250,257 @@ __global__ void __launch_bounds__(kXThreads, 1) cross_attn_fwd_tc_kernel(const X
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(X::TCOLS_FWD) : "memory");
+  }
+}
+
+// ================================================================================================================
+// backward with respect to Q only: the text K / V come from frozen projections of a constant prompt embedding
+// (reference t2v_video_sample.py:67-68; utils/motionclone_functions.py:236 differentiates w.r.t. the latents), so
+// dK and dV are never needed on this path.
+//   S = Q K^T, dP = dO V^T            (two tcgen05.mma chains, one commit)
+//   P = softmax(scale S)  (recomputed, same arithmetic as the forward), D = sum_j P_j dP_j
+//   dS = scale * P o (dP - D) -> fp16 -> shared memory
+//   dQ = dS K                          (A = dS K-major, B = K MN-major: the SAME shared-memory tile as the K-major
+//                                       operand of Q K^T, read through a different descriptor)
+// ================================================================================================================
+template <int DH>
+__global__ void __launch_bounds__(kXThreads) cross_attn_bwd_dq_tc_kernel(const XAParams prm) {
+  using X = XACfg<DH>;
+  constexpr int DHP = X::DHP, KCQ = X::KCQ;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
+  uint8_t* sQ = smem + 128;            // K-major [KCQ][128][16 B]
+  uint8_t* sD = sQ + X::Q_BYTES;       // dO, K-major [KCQ][128][16 B]
+  uint8_t* sK = sD + X::Q_BYTES;       // [KCQ][80][16 B]: K-major for Q K^T, MN-major for dS K
+  uint8_t* sV = sK + X::KV_BYTES;      // [KCQ][80][16 B]: K-major for dO V^T
+  uint8_t* sS = sV + X::KV_BYTES;      // dS, K-major [10][128][16 B]
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, qt = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * kXM;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(X::TCOLS_BWD)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+
+  stage_chunks<DH, KCQ, kXM>(sQ, prm.q + (int64_t)b * prm.q_sb + h * DH, prm.q_sr, q0, prm.Nq, kXM, tid);
+  stage_chunks<DH, KCQ, kXM>(sD, prm.d_o + (int64_t)b * prm.do_sb + h * DH, prm.do_sr, q0, prm.Nq, kXM, tid);
+  stage_chunks<DH, KCQ, kXN>(sK, prm.k + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, kXN, tid);
+  stage_chunks<DH, KCQ, kXN>(sV, prm.v + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, kXN, tid);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- S = Q K^T -> [0, 80);  dP = dO V^T -> [96, 176) ----
+  if (tid == 0) {
+    const uint32_t idesc = umma_instr_desc_f16(kXM, kXN, false);
+#pragma unroll
+    for (int ks = 0; ks < X::KS1; ++ks) {
+      const uint64_t a = umma_smem_desc(smem_u32(sQ) + ks * 2 * kXM * 16, kXM * 16, 128);
+      const uint64_t bd = umma_smem_desc(smem_u32(sK) + ks * 2 * kXN * 16, kXN * 16, 128);
+      umma_f16(tmem_base, a, bd, idesc, ks > 0 ? 1u : 0u);
+    }
+#pragma unroll
+    for (int ks = 0; ks < X::KS1; ++ks) {
+      const uint64_t a = umma_smem_desc(smem_u32(sD) + ks * 2 * kXM * 16, kXM * 16, 128);
+      const uint64_t bd = umma_smem_desc(smem_u32(sV) + ks * 2 * kXN * 16, kXN * 16, 128);
+      umma_f16(tmem_base + X::DP_COL, a, bd, idesc, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+
+  // ---- row `tid`: P (recomputed), D = sum_j P_j dP_j, dS = scale * P (dP - D) -> fp16 -> sS ----
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  {
+    uint32_t ph[kXN / 2];
+    softmax_row_tmem(lane_addr, prm.Nk, prm.scale, ph);
+    float dsum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kXN / 16; ++c) {
+      uint32_t r[16];
+      tmem_ld16(lane_addr + X::DP_COL + c * 16, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 p2 = __half22float2(*reinterpret_cast<const __half2*>(&ph[c * 8 + j]));
+        dsum = fmaf(p2.x, __uint_as_float(r[2 * j]), dsum);
+        dsum = fmaf(p2.y, __uint_as_float(r[2 * j + 1]), dsum);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kXN / 16; ++c) {
+      uint32_t r[16];
+      tmem_ld16(lane_addr + X::DP_COL + c * 16, r);
+      tmem_ld_wait();
+      uint32_t ds[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 p2 = __half22float2(*reinterpret_cast<const __half2*>(&ph[c * 8 + j]));
+        ds[j] = pack_half2(prm.scale * p2.x * (__uint_as_float(r[2 * j]) - dsum),
+                           prm.scale * p2.y * (__uint_as_float(r[2 * j + 1]) - dsum));
+      }
+      *reinterpret_cast<uint4*>(sS + ((2 * c) * kXM + tid) * 16) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+      *reinterpret_cast<uint4*>(sS + ((2 * c + 1) * kXM + tid) * 16) = make_uint4(ds[4], ds[5], ds[6], ds[7]);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();  // all reads of S and dP are complete: dQ may overwrite their columns
+  tc_fence_after();
+
+  // ---- dQ = dS K ----
+  if (tid == 0) {
+    const uint32_t idesc = umma_instr_desc_f16(kXM, DHP, true);
+#pragma unroll
+    for (int ks = 0; ks < X::KS2; ++ks) {
+      const uint64_t a = umma_smem_desc(smem_u32(sS) + ks * 2 * kXM * 16, kXM * 16, 128);
+      const uint64_t bd = umma_smem_desc(smem_u32(sK) + ks * 2 * 128, 128, kXN * 16);
+      umma_f16(tmem_base, a, bd, idesc, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 1);
+  tc_fence_after();
+
+  {
+    const int row = q0 + tid;
+    __half* orow = prm.o + (int64_t)b * prm.o_sb + (int64_t)row * prm.o_sr + h * DH;
+#pragma unroll
+    for (int c = 0; c < DHP / 16; ++c) {
+      uint32_t r[16];
+      tmem_ld16(lane_addr + c * 16, r);
+      tmem_ld_wait();
+      if (row < prm.Nq) {
+#pragma unroll
+        for (int half8 = 0; half8 < 2; ++half8) {
+          if (c * 16 + half8 * 8 < DH) {
+            uint4 pk;
+            pk.x = pack_half2(__uint_as_float(r[half8 * 8 + 0]), __uint_as_float(r[half8 * 8 + 1]));
+            pk.y = pack_half2(__uint_as_float(r[half8 * 8 + 2]), __uint_as_float(r[half8 * 8 + 3]));
+            pk.z = pack_half2(__uint_as_float(r[half8 * 8 + 4]), __uint_as_float(r[half8 * 8 + 5]));
+            pk.w = pack_half2(__uint_as_float(r[half8 * 8 + 6]), __uint_as_float(r[half8 * 8 + 7]));
+            *reinterpret_cast<uint4*>(orow + c * 16 + half8 * 8) = pk;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(X::TCOLS_BWD) : "memory");
   }
 }
 
 template <int DH>
 static int launch_xattn(const XAParams& prm, cudaStream_t st) {
-  constexpr int DHP = (DH + 15) / 16 * 16;
-  constexpr int KCQ = DHP / 8;
-  const int smem = 128 + KCQ * kXM * 16 + 2 * KCQ * kXN * 16 + (kXN / 8) * kXM * 16;
+  const int smem = XACfg<DH>::SMEM_FWD;
   auto kern = cross_attn_fwd_tc_kernel<DH>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  dim3 grid((prm.Nq + kXM - 1) / kXM, prm.H, prm.B);
+  dim3 grid(prm.H, (prm.Nq + kXM - 1) / kXM, prm.B);
   kern<<<grid, kXThreads, smem, st>>>(prm);
   count_launch();
   return check_launch("cross_attn_fwd_tc");
 }
 
+template <int DH>
+static int launch_xattn_bwd(const XAParams& prm, cudaStream_t st) {
+  const int smem = XACfg<DH>::SMEM_BWD;
+  auto kern = cross_attn_bwd_dq_tc_kernel<DH>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  dim3 grid(prm.H, (prm.Nq + kXM - 1) / kXM, prm.B);
+  kern<<<grid, kXThreads, smem, st>>>(prm);
+  count_launch();
+  return check_launch("cross_attn_bwd_dq_tc");
+}
+
+static int xattn_check(const char* what, const void* q, const void* k, const void* v, const void* o, int B, int Nq, int Nk,
+                       int H, int64_t strides_or) {
+  if (!q || !k || !v || !o || B <= 0 || Nq <= 0 || Nk <= 0 || H <= 0) {
+    set_error("%s: null pointer or non-positive dims", what);
+    return MC_E_INVALID;
+  }
+  if (Nk > kXN) {
+    set_error("%s: at most %d keys (text tokens) per tile, got %d", what, kXN, Nk);
+    return MC_E_UNSUPPORTED;
+  }
+  if (B > 65535 || (Nq + kXM - 1) / kXM > 65535) {
+    set_error("%s: grid too large (B <= 65535, Nq <= 65535 * 128)", what);
+    return MC_E_UNSUPPORTED;
+  }
+  if (strides_or % 8 != 0) {
+    set_error("%s: strides must be multiples of 8 elements (16-byte rows)", what);
+    return MC_E_INVALID;
+  }
+  return MC_OK;
+}
+
 }  // namespace mc
+
+#define MC_XATTN_DISPATCH(FN)                       \
+  switch (DH) {                                     \
+    case 16: return FN<16>(prm, st);                \
+    case 32: return FN<32>(prm, st);                \
+    case 40: return FN<40>(prm, st);                \
+    case 64: return FN<64>(prm, st);                \
+    case 80: return FN<80>(prm, st);                \
+    case 160: return FN<160>(prm, st);              \
+    default: break;                                 \
+  }
 
 extern "C" int mc_cross_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int Nq, int Nk, int H, int DH,
                                  int64_t q_stride_b, int64_t q_stride_row, int64_t kv_stride_b, int64_t kv_stride_row,
                                  int64_t o_stride_b, int64_t o_stride_row, float scale, void* stream) {
   using namespace mc;
-  if (!q || !k || !v || !o || B <= 0 || Nq <= 0 || Nk <= 0 || H <= 0) {
-    set_error("cross_attn_fwd: null pointer or non-positive dims");
-    return MC_E_INVALID;
-  }
-  if (Nk > kXN) {
-    set_error("cross_attn_fwd: at most %d keys (text tokens) per tile, got %d", kXN, Nk);
-    return MC_E_UNSUPPORTED;
-  }
-  if ((q_stride_row | kv_stride_row | o_stride_row | q_stride_b | kv_stride_b | o_stride_b) % 8 != 0) {
-    set_error("cross_attn_fwd: strides must be multiples of 8 elements (16-byte rows)");
-    return MC_E_INVALID;
-  }
-  XAParams prm{(const __half*)q, (const __half*)k, (const __half*)v, (__half*)o, q_stride_b, q_stride_row, kv_stride_b,
-               kv_stride_row, o_stride_b, o_stride_row, B, Nq, Nk, H, scale};
+  const int rc = xattn_check("cross_attn_fwd", q, k, v, o, B, Nq, Nk, H,
+                             q_stride_row | kv_stride_row | o_stride_row | q_stride_b | kv_stride_b | o_stride_b);
+  if (rc != MC_OK) return rc;
+  XAParams prm{};
+  prm.q = (const __half*)q, prm.k = (const __half*)k, prm.v = (const __half*)v, prm.o = (__half*)o;
+  prm.q_sb = q_stride_b, prm.q_sr = q_stride_row, prm.kv_sb = kv_stride_b, prm.kv_sr = kv_stride_row;
+  prm.o_sb = o_stride_b, prm.o_sr = o_stride_row;
+  prm.B = B, prm.Nq = Nq, prm.Nk = Nk, prm.H = H, prm.scale = scale;
   cudaStream_t st = (cudaStream_t)stream;
-  switch (DH) {
-    case 40: return launch_xattn<40>(prm, st);
-    case 80: return launch_xattn<80>(prm, st);
-    case 160: return launch_xattn<160>(prm, st);
-    case 16: return launch_xattn<16>(prm, st);
-    case 32: return launch_xattn<32>(prm, st);
-    case 64: return launch_xattn<64>(prm, st);
-    default: break;
-  }
+  MC_XATTN_DISPATCH(launch_xattn)
   set_error("cross_attn_fwd: unsupported head dim %d (16, 32, 40, 64, 80, 160)", DH);
+  return MC_E_UNSUPPORTED;
+}
+
+extern "C" int mc_cross_attn_bwd_dq(const void* q, const void* k, const void* v, const void* d_o, void* dq, int B, int Nq,
+                                    int Nk, int H, int DH, int64_t q_stride_b, int64_t q_stride_row, int64_t kv_stride_b,
+                                    int64_t kv_stride_row, int64_t do_stride_b, int64_t do_stride_row,
+                                    int64_t dq_stride_b, int64_t dq_stride_row, float scale, void* stream) {
+  using namespace mc;
+  const int rc = xattn_check("cross_attn_bwd_dq", q, k, v, dq, B, Nq, Nk, H,
+                             q_stride_row | kv_stride_row | dq_stride_row | q_stride_b | kv_stride_b | dq_stride_b |
+                                 do_stride_b | do_stride_row);
+  if (rc != MC_OK) return rc;
+  if (!d_o) {
+    set_error("cross_attn_bwd_dq: null d_o");
+    return MC_E_INVALID;
+  }
+  XAParams prm{};
+  prm.q = (const __half*)q, prm.k = (const __half*)k, prm.v = (const __half*)v, prm.d_o = (const __half*)d_o;
+  prm.o = (__half*)dq;
+  prm.q_sb = q_stride_b, prm.q_sr = q_stride_row, prm.kv_sb = kv_stride_b, prm.kv_sr = kv_stride_row;
+  prm.o_sb = dq_stride_b, prm.o_sr = dq_stride_row, prm.do_sb = do_stride_b, prm.do_sr = do_stride_row;
+  prm.B = B, prm.Nq = Nq, prm.Nk = Nk, prm.H = H, prm.scale = scale;
+  cudaStream_t st = (cudaStream_t)stream;
+  MC_XATTN_DISPATCH(launch_xattn_bwd)
+  set_error("cross_attn_bwd_dq: unsupported head dim %d (16, 32, 40, 64, 80, 160)", DH);
   return MC_E_UNSUPPORTED;
 }

@@ -17,6 +17,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "mc_common.cuh"
 
 namespace mc {
@@ -49,6 +51,18 @@ struct TileGeom {
   int x_bytes;         // bytes of the extra tile
 };
 
+// Compile-time twin of TileGeom for the tile shapes the SD1.5 UNet actually produces (P = 1; all 8 heads as one fused
+// Q|K|V run, or a 2/4-head group staged per tensor): every shared-memory address in the item loop becomes an immediate,
+// and the item -> (position, head) split needs no integer division. Any other shape runs on the runtime TileGeom.
+constexpr int pad16c(int row_bytes) { return row_bytes + ((16 - (row_bytes % 128)) + 128) % 128; }
+
+template <int DH, int L, int P_, int HG_, bool FUSED>
+struct CGeom {
+  static constexpr int P = P_, HG = HG_, W = HG_ * DH, PS = FUSED ? 3 * HG_ * DH : HG_ * DH, fused = FUSED ? 1 : 0;
+  static constexpr int pitch = pad16c(P_ * PS * 2), pitch_x = pad16c(P_ * W * 2);
+  static constexpr int tensor_bytes = (L * pitch + 127) / 128 * 128, x_bytes = (L * pitch_x + 127) / 128 * 128;
+};
+
 struct TAParams {
   const __half *q, *k, *v;
   const __half* d_o;          // bwd only
@@ -70,14 +84,14 @@ struct TAParams {
 // L >= 16: idx is the frame.  L == 8: two positions are packed, idx = 8*(position in pair) + frame; when the tile
 // holds an odd number of positions the last one is paired with itself (duplicate rows compute and store identical
 // values).
-template <int L>
-__device__ __forceinline__ uint32_t vrow_off(int idx, int pl0, const TileGeom& g) {
+template <int L, typename G>
+__device__ __forceinline__ uint32_t vrow_off(int idx, int pl0, const G& g) {
   if (L == 8) return (idx & 7) * g.pitch + (min(pl0 + (idx >> 3), g.P - 1) * g.PS) * 2;  // odd tail: pair with itself
   return idx * g.pitch + (pl0 * g.PS) * 2;
 }
 // same for the extra (dO / dQ) tile of the backward, whose rows are always P*W halfs
-template <int L>
-__device__ __forceinline__ uint32_t xrow_off(int idx, int pl0, const TileGeom& g) {
+template <int L, typename G>
+__device__ __forceinline__ uint32_t xrow_off(int idx, int pl0, const G& g) {
   if (L == 8) return (idx & 7) * g.pitch_x + (min(pl0 + (idx >> 3), g.P - 1) * g.W) * 2;
   return idx * g.pitch_x + (pl0 * g.W) * 2;
 }
@@ -112,15 +126,15 @@ __device__ __forceinline__ void store_rows(__half* gdst, const uint8_t* ssrc, in
 }
 
 // S[mt] = Q K^T for one 16-row query tile: s[nt][0..3] in the m16n8 accumulator layout.
-template <int L, bool X>
-__device__ __forceinline__ uint32_t row_off(int idx, int pl0, const TileGeom& g) {
+template <int L, bool X, typename G>
+__device__ __forceinline__ uint32_t row_off(int idx, int pl0, const G& g) {
   return X ? xrow_off<L>(idx, pl0, g) : vrow_off<L>(idx, pl0, g);
 }
 
 // AX / BX: operand lives in the extra (dO) tile rather than in the Q/K/V tile(s)
-template <typename C, bool AX = false, bool BX = false>
+template <typename C, bool AX = false, bool BX = false, typename G>
 __device__ __forceinline__ void qk_scores(float (&s)[C::NKT][4], uint32_t sQ, uint32_t sK, int mt, int pl0,
-                                          int colbase, const TileGeom& g, int lane) {
+                                          int colbase, const G& g, int lane) {
 #pragma unroll
   for (int nt = 0; nt < C::NKT; ++nt)
 #pragma unroll
@@ -192,19 +206,28 @@ __device__ __forceinline__ void softmax_rows(float (&s)[C::NKT][4], float scale)
       z[e] += __shfl_xor_sync(0xffffffffu, z[e], 1);
     }
     const float sum = z[0] + z[1];
+    // x / sum, correctly rounded, with ONE reciprocal per row: y = RN(1/sum), q = RN(x y), r = x - q sum (exact, fma),
+    // q' = RN(q + r y) is RN(x / sum) (Markstein) for the operands that occur here (1 <= sum <= L, 0 <= x <= 1; an x so
+    // small that r underflows gives an fp16 zero either way). Bit-identical to ATen's `exp(x - max) / sum` and ~2x
+    // fewer instructions than L independent IEEE divisions.
+    const float y = __frcp_rn(sum);
 #pragma unroll
     for (int nt = 0; nt < C::NKT; ++nt) {
       const bool valid = (C::L != 8) || (nt == hf);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) s[nt][2 * hf + e] = valid ? round_half(x[nt][e] / sum) : 0.f;
+      for (int e = 0; e < 2; ++e) {
+        const float q0 = x[nt][e] * y;
+        const float q1 = fmaf(fmaf(-q0, sum, x[nt][e]), y, q0);
+        s[nt][2 * hf + e] = valid ? round_half(q1) : 0.f;
+      }
     }
   }
 }
 
 // acc[nd][.] += A(16 x keys, register fragments pa[kk][0..3]) * T(keys x DH) with T row-major in smem (V, K, Q, dO)
-template <typename C, bool TX = false>
+template <typename C, bool TX = false, typename G>
 __device__ __forceinline__ void mma_a_rowmajor_b(float (&acc)[C::NDT][4], const uint32_t (&pa)[C::KK][4],
-                                                 uint32_t sT, int pl0, int colbase, const TileGeom& g, int lane) {
+                                                 uint32_t sT, int pl0, int colbase, const G& g, int lane) {
   const int m = lane >> 3, r8 = lane & 7;
 #pragma unroll
   for (int kk = 0; kk < C::KK; ++kk) {
@@ -226,9 +249,9 @@ __device__ __forceinline__ void mma_a_rowmajor_b(float (&acc)[C::NDT][4], const 
 }
 
 // write a 16 x DH fp32 accumulator tile (query/key tile mt) as fp16 into a staged tensor, scaled by `mul`
-template <typename C, bool TX = false>
+template <typename C, bool TX = false, typename G>
 __device__ __forceinline__ void store_acc(const float (&acc)[C::NDT][4], float mul, uint8_t* sT_generic, int mt,
-                                          int pl0, int colbase, const TileGeom& g, int lane) {
+                                          int pl0, int colbase, const G& g, int lane) {
   const int gq = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf) {
@@ -264,8 +287,8 @@ __device__ __forceinline__ int64_t out_row(int b, int p_first, int p_last, int h
 // ================================================================================================================
 // One (position[-pair], head) item of the forward: scores, softmax, per-row by-products, O = P V over the item's Q rows.
 // `bar_v` (nullable): barrier of a separately staged V, waited on first use.
-template <typename C>
-__device__ __forceinline__ void fwd_item(const TAParams& prm, const TileGeom& g, uint8_t* sQ, uint32_t sQa, uint32_t sKa,
+template <typename C, typename G>
+__device__ __forceinline__ void fwd_item(const TAParams& prm, const G& g, uint8_t* sQ, uint32_t sQa, uint32_t sKa,
                                          uint32_t sVa, int b, int p0, int h0, int item, int lane, bool has_o,
                                          uint64_t* bar_v, bool& v_ready) {
   constexpr int DH = C::DH;
@@ -358,13 +381,22 @@ __device__ __forceinline__ void fwd_item(const TAParams& prm, const TileGeom& g,
   }
 }
 
-template <int DH, int L, int NW>
+template <typename G>
+__device__ __forceinline__ G load_geom(const TAParams& prm) {
+  if constexpr (std::is_same<G, TileGeom>::value) {
+    return prm.g;
+  } else {
+    return G{};
+  }
+}
+
+template <int DH, int L, int NW, typename G = TileGeom>
 __global__ void __launch_bounds__(NW * 32) temporal_attn_fwd_kernel(const TAParams prm) {
   using C = TACfg<DH, L>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem);
   uint64_t* bar_v = bar_qk + 1;
-  const TileGeom g = prm.g;
+  const G g = load_geom<G>(prm);
   uint8_t* sQ = smem + kHeaderBytes;
   uint8_t* sK = g.fused ? sQ + g.W * 2 : sQ + g.tensor_bytes;       // fused: K, V are column offsets of one tile
   uint8_t* sV = g.fused ? sQ + g.W * 4 : sQ + 2 * g.tensor_bytes;
@@ -537,14 +569,14 @@ __global__ void __launch_bounds__((NCW + 1) * 32) temporal_attn_fwd_persistent_k
 // backward: dq, dk, dv from d_o and/or the probability branches. Staged: Q, K, V, dO; outputs reuse dead tiles
 // (dV -> V, dQ -> dO, dK -> K).
 // ================================================================================================================
-template <int DH, int L, int NW>
+template <int DH, int L, int NW, typename G = TileGeom>
 __global__ void __launch_bounds__(NW * 32) temporal_attn_bwd_kernel(const TAParams prm) {
   using C = TACfg<DH, L>;
   static_assert(C::MT == 1 || L == 32, "");
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem);
   uint64_t* bar_v = bar_qk + 1;
-  const TileGeom g = prm.g;
+  const G g = load_geom<G>(prm);
   uint8_t* sQ = smem + kHeaderBytes;
   uint8_t* sK = g.fused ? sQ + g.W * 2 : sQ + g.tensor_bytes;
   uint8_t* sV = g.fused ? sQ + g.W * 4 : sQ + 2 * g.tensor_bytes;
@@ -825,6 +857,58 @@ static int launch_fwd_persistent(TAParams& prm, int n_tiles, cudaStream_t st) {
   return check_launch("temporal_attn_fwd(persistent)");
 }
 
+// Does the runtime geometry equal the compile-time one (then the constant-address kernel can take the launch)?
+template <typename G>
+static bool geom_matches(const TileGeom& g) {
+  return g.P == G::P && g.HG == G::HG && g.W == G::W && g.PS == G::PS && g.fused == G::fused && g.pitch == G::pitch &&
+         g.pitch_x == G::pitch_x && g.tensor_bytes == G::tensor_bytes && g.x_bytes == G::x_bytes;
+}
+
+// The tile shapes of the SD1.5 + motion-module UNet (8 heads; DH = 40 / 80 / 160; L = 16 or 32), see CGeom.
+template <int DH, int L>
+struct CGeomSet {
+  static constexpr bool enabled = (DH == 40 || DH == 80 || DH == 160) && (L == 16 || L == 32);
+  using Fused8 = CGeom<DH, L, 1, 8, true>;   // all 8 heads, one Q|K|V run per frame
+  using Sep4 = CGeom<DH, L, 1, 4, false>;    // 4-head group, Q / K / V staged separately
+  using Sep2 = CGeom<DH, L, 1, 2, false>;
+};
+
+template <int DH, int L, typename G, bool BWD>
+static void launch_cgeom(const TAParams& prm, unsigned grid, int smem, cudaStream_t st) {
+  if constexpr (BWD) {
+    auto kern = temporal_attn_bwd_kernel<DH, L, 4, G>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kern<<<grid, 4 * 32, smem, st>>>(prm);
+  } else {
+    auto kern = temporal_attn_fwd_kernel<DH, L, 4, G>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kern<<<grid, 4 * 32, smem, st>>>(prm);
+  }
+}
+
+// true if a constant-geometry instantiation took the launch (4-warp CTAs only: these tiles hold <= 8 items)
+template <int DH, int L, bool BWD>
+static bool try_launch_cgeom(const TAParams& prm, unsigned grid, int smem, int n_items, cudaStream_t st) {
+  static const int env_off = getenv("MC_NO_CGEOM") ? atoi(getenv("MC_NO_CGEOM")) : 0;  // A/B knob for profiling
+  if constexpr (CGeomSet<DH, L>::enabled) {
+    using S = CGeomSet<DH, L>;
+    if (env_off || n_items >= 16 || prm.H != 8) return false;
+    if (geom_matches<typename S::Fused8>(prm.g)) {
+      launch_cgeom<DH, L, typename S::Fused8, BWD>(prm, grid, smem, st);
+      return true;
+    }
+    if (geom_matches<typename S::Sep4>(prm.g)) {
+      launch_cgeom<DH, L, typename S::Sep4, BWD>(prm, grid, smem, st);
+      return true;
+    }
+    if (geom_matches<typename S::Sep2>(prm.g)) {
+      launch_cgeom<DH, L, typename S::Sep2, BWD>(prm, grid, smem, st);
+      return true;
+    }
+  }
+  return false;
+}
+
 template <int DH, int L>
 static int launch_fwd(TAParams& prm, cudaStream_t st) {
   choose_geom(prm.D, L, prm.H, DH, 3, L == 8, is_fusable(prm, prm.H * DH) && prm.o != nullptr, &prm.g);
@@ -841,7 +925,8 @@ static int launch_fwd(TAParams& prm, cudaStream_t st) {
     if (rc <= 0) return rc;
   }
   static const int env_nw = getenv("MC_WARPS") ? atoi(getenv("MC_WARPS")) : 0;  // tuning knob
-  if (env_nw ? env_nw == 8 : n_items >= 16) {
+  if (!env_nw && try_launch_cgeom<DH, L, false>(prm, (unsigned)grid, smem, n_items, st)) {
+  } else if (env_nw ? env_nw == 8 : n_items >= 16) {
     auto kern = temporal_attn_fwd_kernel<DH, L, 8>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     kern<<<(unsigned)grid, 8 * 32, smem, st>>>(prm);
@@ -860,7 +945,8 @@ static int launch_bwd(TAParams& prm, cudaStream_t st) {
   const int smem = tile_smem(prm.g, 4);
   const int64_t grid = (int64_t)prm.B * (prm.D / prm.g.P) * (prm.H / prm.g.HG);
   const int n_items = ((prm.g.P + TACfg<DH, L>::PP - 1) / TACfg<DH, L>::PP) * prm.g.HG;
-  if (n_items >= 16) {
+  if (try_launch_cgeom<DH, L, true>(prm, (unsigned)grid, smem, n_items, st)) {
+  } else if (n_items >= 16) {
     auto kern = temporal_attn_bwd_kernel<DH, L, 8>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     kern<<<(unsigned)grid, 8 * 32, smem, st>>>(prm);

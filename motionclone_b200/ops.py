@@ -487,18 +487,63 @@ class BiasResidualAddFn(torch.autograd.Function):
         return g, g, None
 
 
-def cross_attention_forward(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float) -> Tensor:
-    """tcgen05 text cross-attention (csrc/cross_attn_tc.cu): q [B, Nq, C], k / v [B, Nk <= 80, C] -> [B, Nq, C]."""
+def _check_xattn(q: Tensor, k: Tensor, v: Tensor) -> None:
     for name, t in (("q", q), ("k", k), ("v", v)):
         _require(t, name)
         if t.dim() != 3 or t.stride(2) != 1:
             raise ValueError(f"{name} must be [B, N, C] with contiguous channels")
     if k.shape != v.shape or k.stride() != v.stride():
         raise ValueError("k and v must share shape and strides")
+
+
+def cross_attention_forward(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float) -> Tensor:
+    """tcgen05 text cross-attention (csrc/cross_attn_tc.cu): q [B, Nq, C], k / v [B, Nk <= 80, C] -> [B, Nq, C]."""
+    _check_xattn(q, k, v)
     B, Nq, C = q.shape
     o = torch.empty((B, Nq, C), dtype=q.dtype, device=q.device)
+    ev0 = TIMER.start() if TIMER is not None else None
     st = _lib.lib().mc_cross_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), B, Nq, k.shape[1], heads, C // heads,
                                       q.stride(0), q.stride(1), k.stride(0), k.stride(1), o.stride(0), o.stride(1),
                                       float(scale), _stream())
     _lib.check(st, "mc_cross_attn_fwd")
+    if ev0 is not None:  # algorithmic bytes: Q read + O written (K, V are 77 rows)
+        TIMER.stop("cross_attn_fwd", 2 * B * Nq * C * 2, ev0)
     return o
+
+
+def cross_attention_backward(q: Tensor, k: Tensor, v: Tensor, d_o: Tensor, heads: int, scale: float) -> Tensor:
+    """dQ of the text cross-attention (the text K / V carry no gradient on this path): q, d_o [B, Nq, C] -> dq."""
+    _check_xattn(q, k, v)
+    _require(d_o, "d_o")
+    if d_o.shape != q.shape:
+        raise ValueError("d_o must have q's shape")
+    if d_o.stride(2) != 1:
+        d_o = d_o.contiguous()
+    B, Nq, C = q.shape
+    dq = torch.empty((B, Nq, C), dtype=q.dtype, device=q.device)
+    ev0 = TIMER.start() if TIMER is not None else None
+    st = _lib.lib().mc_cross_attn_bwd_dq(_ptr(q), _ptr(k), _ptr(v), _ptr(d_o), _ptr(dq), B, Nq, k.shape[1], heads,
+                                         C // heads, q.stride(0), q.stride(1), k.stride(0), k.stride(1), d_o.stride(0),
+                                         d_o.stride(1), dq.stride(0), dq.stride(1), float(scale), _stream())
+    _lib.check(st, "mc_cross_attn_bwd_dq")
+    if ev0 is not None:  # Q, dO read + dQ written
+        TIMER.stop("cross_attn_bwd", 3 * B * Nq * C * 2, ev0)
+    return dq
+
+
+class CrossAttentionTC(torch.autograd.Function):
+    """o = softmax(scale q k^T) v on the tcgen05 kernels, differentiable w.r.t. q only (see mc_cross_attn_bwd_dq)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads: int, scale: float):
+        ctx.save_for_backward(q, k, v)
+        ctx.heads, ctx.scale = heads, scale
+        return cross_attention_forward(q, k, v, heads, scale)
+
+    @staticmethod
+    def backward(ctx, d_o):
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise NotImplementedError("cross-attention gradients w.r.t. the text K / V are not on the MotionClone path "
+                                      "(frozen projections of a constant prompt embedding)")
+        q, k, v = ctx.saved_tensors
+        return cross_attention_backward(q, k, v, d_o, ctx.heads, ctx.scale), None, None, None, None

@@ -9,10 +9,12 @@ Design differences (B200-first):
   checkpoint, `use_linear_projection=False`) run as GEMMs on that view;
 * self-attention projects q,k,v with one GEMM; cross-attention projects the text K/V ONCE per prompt, not once per
   frame (the reference repeats the text f times, attention.py:100, and re-projects it for every frame);
-* the softmax(QK^T)V core at the reference's xformers seam (`_memory_efficient_attention_xformers`, :535-542) is
+* text cross-attention (`attn2`) runs on this package's tcgen05 / TMEM kernels (csrc/cross_attn_tc.cu), forward and
+  the gradient w.r.t. the queries (the text K / V carry no gradient on the MotionClone path);
+* spatial SELF-attention at the reference's xformers seam (`_memory_efficient_attention_xformers`, :535-542) is
   dispatched to `F.scaled_dot_product_attention` (flash kernels, LIBRARY code, same published semantics as
-  xformers.ops.memory_efficient_attention). The hand-written tcgen05 replacement for this seam is the next §8 row;
-  it is not claimed as this package's kernel (DESIGN.md §5).
+  xformers.ops.memory_efficient_attention). The hand-written tcgen05 replacement for that seam is the next §8 row;
+  it is not claimed as this package's kernel (DESIGN.md §4).
 """
 from __future__ import annotations
 
@@ -23,6 +25,9 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
+
+
+_XATTN_TC_HEAD_DIMS = (16, 32, 40, 64, 80, 160)  # instantiations of csrc/cross_attn_tc.cu
 
 
 def _frozen(*params) -> bool:
@@ -126,6 +131,7 @@ class CrossAttention(nn.Module):
         self.to_v = nn.Linear(cross_attention_dim, inner_dim, bias=bias)
         self.to_out = nn.ModuleList([nn.Linear(inner_dim, query_dim), nn.Dropout(dropout)])
         self._fused = None
+        self._fused_kv = None
 
     # ---- reference helpers kept for drop-in use (attention.py:367-385, :544-562) ----
     def reshape_heads_to_batch_dim(self, tensor):
@@ -154,6 +160,14 @@ class CrossAttention(nn.Module):
         if self._fused is None or self._fused[0] != key:
             self._fused = (key, torch.cat([w.detach() for w in ws], dim=0).contiguous())
         return self._fused[1]
+
+    def fused_kv_weight(self) -> torch.Tensor:
+        """[2C, c_text] concatenation of to_k/to_v (cross-attention: one GEMM projects the text K | V)."""
+        ws = (self.to_k.weight, self.to_v.weight)
+        key = tuple((w.data_ptr(), w._version, w.dtype, w.device) for w in ws)
+        if self._fused_kv is None or self._fused_kv[0] != key:
+            self._fused_kv = (key, torch.cat([w.detach() for w in ws], dim=0).contiguous())
+        return self._fused_kv[1]
 
     def get_attention_scores(self, query, key, attention_mask=None):
         """attention.py:564-611: query/key `[B*heads, S, dh]` -> probabilities in the input dtype. For temporal
@@ -203,11 +217,20 @@ class CrossAttention(nn.Module):
             if bf % b:
                 raise ValueError("encoder_hidden_states batch must divide the frame batch")
             f = bf // b
-            q = self.to_q(hidden_states).view(b, f * n, h, dh).transpose(1, 2)        # frames of one prompt share K/V
-            k = self.to_k(ctx).view(b, -1, h, dh).transpose(1, 2)
-            v = self.to_v(ctx).view(b, -1, h, dh).transpose(1, 2)
-            o = F.scaled_dot_product_attention(q, k, v, scale=self.scale)
-            o = o.transpose(1, 2).reshape(bf, n, inner)
+            q = self.to_q(hidden_states).view(b, f * n, inner)                        # frames of one prompt share K/V
+            kv = F.linear(ctx, self.fused_kv_weight())                                # [b, 77, 2C]: K | V column blocks
+            k, v = kv[..., :inner], kv[..., inner:]
+            if ops.glue_kernels_ok(q) and ctx.shape[1] <= 80 and dh in _XATTN_TC_HEAD_DIMS and not kv.requires_grad:
+                # tcgen05 / TMEM kernels (csrc/cross_attn_tc.cu); dQ only: the text K / V carry no gradient here
+                if torch.is_grad_enabled() and q.requires_grad:
+                    o = ops.CrossAttentionTC.apply(q, k, v, h, self.scale)
+                else:
+                    o = ops.cross_attention_forward(q, k, v, h, self.scale)
+                o = o.view(bf, n, inner)
+            else:  # trainable text branch / long contexts: library kernel at the xformers seam
+                q4, k4, v4 = (t.reshape(b, -1, h, dh).transpose(1, 2) for t in (q, k, v))
+                o = F.scaled_dot_product_attention(q4, k4, v4, scale=self.scale)
+                o = o.transpose(1, 2).reshape(bf, n, inner)
         return self.to_out[1](self.to_out[0](o))
 
 

@@ -436,3 +436,45 @@ def test_cross_attention_tcgen05(B, Nq, Nk, H, DH):
     err, err_lib = (o.float() - ref).abs().max().item(), (lib.float() - ref).abs().max().item()
     # P is rounded to fp16 before PV (as flash kernels do) and O once: a few fp16 ulps of O(1) values
     assert err <= max(3e-3, 2.0 * err_lib), (err, err_lib)
+
+
+@pytest.mark.parametrize("B,Nq,Nk,H,DH", [(1, 256, 77, 8, 40), (2, 1024, 77, 8, 80), (1, 384, 77, 8, 160), (1, 200, 77, 8, 32),
+                                          (1, 4096, 77, 8, 40), (1, 128, 64, 8, 64), (1, 100, 77, 2, 16)])
+def test_cross_attention_tcgen05_backward_dq(B, Nq, Nk, H, DH):
+    """dQ of attn2 (the guided pass differentiates w.r.t. the latents only, utils/motionclone_functions.py:236; the text
+    K / V are constants): against fp32 autograd of the math statement, next to the library flash backward's own error."""
+    ops, dev = _ops(), _dev()
+    C = H * DH
+    g = torch.Generator().manual_seed(7 * Nq + DH)
+    q = torch.randn(B, Nq, C, generator=g).to(dev, torch.float16)
+    kv = torch.randn(B, Nk, 2 * C, generator=g).to(dev, torch.float16)
+    k, v = kv[..., :C], kv[..., C:]
+    d_o = torch.randn(B, Nq, C, generator=g).to(dev, torch.float16)
+    scale = DH ** -0.5
+
+    qf = q.float().requires_grad_(True)
+    qh, kh, vh = (t.reshape(B, -1, H, DH).transpose(1, 2) for t in (qf, k.float(), v.float()))
+    ref_o = (torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1) @ vh).transpose(1, 2).reshape(B, Nq, C)
+    (ref,) = torch.autograd.grad(ref_o, qf, d_o.float())
+
+    qg = q.clone().requires_grad_(True)
+    o = ops.CrossAttentionTC.apply(qg, k, v, H, scale)
+    (dq,) = torch.autograd.grad(o, qg, d_o)
+
+    ql = q.clone().requires_grad_(True)
+    lib_o = torch.nn.functional.scaled_dot_product_attention(
+        *(t.reshape(B, -1, H, DH).transpose(1, 2) for t in (ql, k.contiguous(), v.contiguous())), scale=scale)
+    (lib,) = torch.autograd.grad(lib_o, ql, d_o.reshape(B, Nq, H, DH).transpose(1, 2))
+    err, err_lib = (dq.float() - ref).abs().max().item(), (lib.float() - ref).abs().max().item()
+    assert torch.isfinite(dq).all()
+    assert err <= max(5e-3 * ref.abs().max().item(), 2.0 * err_lib), (err, err_lib, ref.abs().max().item())
+
+
+def test_cross_attention_tcgen05_rejects_kv_grad():
+    ops, dev = _ops(), _dev()
+    q = torch.randn(1, 128, 64, device=dev, dtype=torch.float16, requires_grad=True)
+    k = torch.randn(1, 77, 64, device=dev, dtype=torch.float16, requires_grad=True)
+    v = torch.randn(1, 77, 64, device=dev, dtype=torch.float16)
+    o = ops.CrossAttentionTC.apply(q, k, v, 2, 32 ** -0.5)
+    with pytest.raises(NotImplementedError):
+        o.float().sum().backward()
