@@ -132,18 +132,30 @@ int mc_cross_attn_bwd_dq(const void* q, const void* k, const void* v, const void
                          int64_t kv_stride_row, int64_t do_stride_b, int64_t do_stride_row, int64_t dq_stride_b,
                          int64_t dq_stride_row, float scale, void* stream);
 
+/*
+ * Spatial self-attention for short sequences on tcgen05 / TMEM (csrc/self_attn_tc.cu): O = softmax(scale * Q K^T) V per
+ * (frame, head) with N <= 256 tokens per frame — the whole key axis is one TMEM tile. Replaces the xformers call for
+ * `attn1` (models/attention.py:190-192, :271-278 -> :535-542) at the 16x16 and 8x8 latent levels in the inference
+ * passes. q, k, v: [B, N, H*DH] views sharing one stride pattern (e.g. column blocks of a fused QKV projection);
+ * strides in elements (multiples of 8); DH in {40, 64, 80, 160}.
+ */
+int mc_self_attn_short_fwd(const void* q, const void* k, const void* v, void* o, int B, int N, int H, int DH,
+                           int64_t qkv_stride_b, int64_t qkv_stride_row, int64_t o_stride_b, int64_t o_stride_row,
+                           float scale, void* stream);
+
 /* out = a + bias[c] + b on channel-innermost fp16 tensors (n elements, C channels): the resnet's residual add
  * `input_tensor + hidden_states` (models/resnet.py:209-211) with conv2's (+ the shortcut conv's) bias folded in. */
 int mc_bias_residual_add(const void* a, const void* b, const void* bias, void* out, int64_t n, int C, void* stream);
 
 /*
- * Memory-bound glue of the UNet3D forward on NHWC / token-major fp16 activations (inference passes only; the
- * autograd-carrying guided pass keeps ATen).
+ * Memory-bound glue of the UNet3D forward (and of the guided pass's backward) on NHWC / token-major fp16 activations.
  *
- * GroupNorm over channels_last x [N, HW, C] (N = batch*frames) with G groups, optional fused SiLU: replaces
- * InflatedGroupNorm + nonlinearity (models/resnet.py:21-29, :186-187, :197-204) and the transformer input norms
- * (models/attention.py:61,105; models/motion_module.py:112,145). Two launches (Welford partials, then apply);
- * workspace >= mc_groupnorm_workspace_bytes(N, G) bytes of device memory.
+ * GroupNorm over channels_last x [N, HW, C] (N = batch*frames, N <= 1024) with G groups, optional fused SiLU
+ * (csrc/groupnorm.cu): replaces InflatedGroupNorm + nonlinearity (models/resnet.py:21-29, :186-187, :197-204) and the
+ * transformer input norms (models/attention.py:61,105; models/motion_module.py:112,145). Two launches: partial
+ * (count, mean, M2) per split, folded into (mean, rstd) by the last CTA of each frame, then apply.
+ * workspace: >= mc_groupnorm_workspace_bytes(N, G) bytes of device memory whose FIRST 4096 BYTES ARE ZERO on first use
+ * (per-frame tickets; every call leaves them zero). One workspace per concurrently running stream.
  */
 int64_t mc_groupnorm_workspace_bytes(int N, int G);
 /* chan_bias (nullable): fp16 [N / frames_per_bias_row, C] added to x before the statistics and the normalisation —
@@ -157,7 +169,8 @@ int mc_groupnorm_nhwc(const void* x, const void* chan_bias, int frames_per_bias_
 int mc_layernorm(const void* x, void* y, const void* gamma, const void* beta, const void* post_add, int rows_per_frame,
                  int frames, int64_t rows, int C, float eps, void* stream);
 /* Backward of the three (input gradients only: weights are frozen on this path, t2v_video_sample.py:67-68).
- * mc_groupnorm_nhwc_stats turns the forward's workspace into stats [N, G, 2] = (mean, rstd) fp32, kept for the backward. */
+ * mc_groupnorm_nhwc_stats copies the forward's finalised statistics out of its workspace: stats [N, G, 2] = (mean, rstd)
+ * fp32, kept for the backward. mc_groupnorm_nhwc_bwd needs its own workspace (same size and zero-ticket rule). */
 int mc_groupnorm_nhwc_stats(const void* workspace, void* stats, int N, int HW, int G, float eps, void* stream);
 int mc_groupnorm_nhwc_bwd(const void* x, const void* chan_bias, int frames_per_bias_row, const void* dz, void* dx,
                           const void* stats, const void* gamma, const void* beta, void* workspace,

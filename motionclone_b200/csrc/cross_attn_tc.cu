@@ -14,60 +14,13 @@
 // DH = 40 is padded to 48 with a zero chunk (K of QK^T and N of PV must be multiples of 16).
 #include <math.h>
 
-#include "mc_common.cuh"
+#include "tc_common.cuh"
 
 namespace mc {
 
 constexpr int kXM = 128;    // query rows per CTA (UMMA M)
 constexpr int kXN = 80;     // padded key count (UMMA N of S, K of PV); 77 text tokens
 constexpr int kXThreads = 128;
-
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  // cute::UMMA::SmemDescriptor: start[0,14) lbo[16,30) sbo[32,46) version[46,48)=1 layout_type[61,64)=0 (no swizzle)
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-
-__device__ __forceinline__ uint32_t umma_instr_desc_f16(int M, int N, bool b_mn_major) {
-  // cute::UMMA::InstrDescriptor: c_format[4,6)=1 (F32), a/b_format = 0 (F16), a_major[15], b_major[16], n>>3 [17,23), m>>4 [24,29)
-  uint32_t d = 0;
-  d |= 1u << 4;
-  d |= (b_mn_major ? 1u : 0u) << 16;
-  d |= (uint32_t)(N >> 3) << 17;
-  d |= (uint32_t)(M >> 4) << 24;
-  return d;
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 struct XAParams {
   const __half *q, *k, *v;
@@ -77,27 +30,6 @@ struct XAParams {
   int B, Nq, Nk, H;
   float scale;
 };
-
-// Stage `nrows` rows (first global row `row0`, rows >= nvalid are zero-filled) of head-columns [0, DH) of a row-major
-// global tensor into the K-major / MN-major no-swizzle chunk layout: 16-byte chunk (row r, chunk c) at (c*R + r)*16.
-// Consecutive threads read consecutive 16-byte chunks of a row (coalesced); chunks >= DH/8 (the K padding) are zeros.
-template <int DH, int KCQ, int R>
-__device__ __forceinline__ void stage_chunks(uint8_t* sdst, const __half* gsrc, int64_t row_stride, int row0, int nvalid,
-                                             int nrows, int tid) {
-  constexpr int KC = DH / 8;  // real chunks per row
-  for (int i = tid; i < nrows * KC; i += kXThreads) {
-    const int r = i / KC, c = i % KC;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (row0 + r < nvalid) val = *reinterpret_cast<const uint4*>(gsrc + (int64_t)(row0 + r) * row_stride + c * 8);
-    *reinterpret_cast<uint4*>(sdst + (c * R + r) * 16) = val;
-  }
-  if (KCQ > KC) {  // zero the padding chunk(s)
-    for (int i = tid; i < nrows * (KCQ - KC); i += kXThreads) {
-      const int r = i % nrows, c = KC + i / nrows;
-      *reinterpret_cast<uint4*>(sdst + (c * R + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
-    }
-  }
-}
 
 // softmax(scale * S) of TMEM lane `lane_addr` over the first nk of 80 columns; result as 40 packed half2 (fp16-rounded
 // probabilities, zeros beyond nk). Same arithmetic in the forward and in the backward's recompute.
@@ -172,9 +104,9 @@ __global__ void __launch_bounds__(kXThreads) cross_attn_fwd_tc_kernel(const XAPa
     fence_mbar_init();
   }
 
-  stage_chunks<DH, KCQ, kXM>(sQ, prm.q + (int64_t)b * prm.q_sb + h * DH, prm.q_sr, q0, prm.Nq, kXM, tid);
-  stage_chunks<DH, KCQ, kXN>(sK, prm.k + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, kXN, tid);
-  stage_chunks<DH, KCQ, kXN>(sV, prm.v + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, kXN, tid);
+  stage_chunks<DH, KCQ, kXM, kXM, kXThreads>(sQ, prm.q + (int64_t)b * prm.q_sb + h * DH, prm.q_sr, q0, prm.Nq, tid);
+  stage_chunks<DH, KCQ, kXN, kXN, kXThreads>(sK, prm.k + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, tid);
+  stage_chunks<DH, KCQ, kXN, kXN, kXThreads>(sV, prm.v + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, tid);
   fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
   tc_fence_before();
   __syncthreads();
@@ -293,10 +225,10 @@ __global__ void __launch_bounds__(kXThreads) cross_attn_bwd_dq_tc_kernel(const X
     fence_mbar_init();
   }
 
-  stage_chunks<DH, KCQ, kXM>(sQ, prm.q + (int64_t)b * prm.q_sb + h * DH, prm.q_sr, q0, prm.Nq, kXM, tid);
-  stage_chunks<DH, KCQ, kXM>(sD, prm.d_o + (int64_t)b * prm.do_sb + h * DH, prm.do_sr, q0, prm.Nq, kXM, tid);
-  stage_chunks<DH, KCQ, kXN>(sK, prm.k + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, kXN, tid);
-  stage_chunks<DH, KCQ, kXN>(sV, prm.v + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, kXN, tid);
+  stage_chunks<DH, KCQ, kXM, kXM, kXThreads>(sQ, prm.q + (int64_t)b * prm.q_sb + h * DH, prm.q_sr, q0, prm.Nq, tid);
+  stage_chunks<DH, KCQ, kXM, kXM, kXThreads>(sD, prm.d_o + (int64_t)b * prm.do_sb + h * DH, prm.do_sr, q0, prm.Nq, tid);
+  stage_chunks<DH, KCQ, kXN, kXN, kXThreads>(sK, prm.k + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, tid);
+  stage_chunks<DH, KCQ, kXN, kXN, kXThreads>(sV, prm.v + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, tid);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();

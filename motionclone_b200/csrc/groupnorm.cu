@@ -1,0 +1,597 @@
+// GroupNorm(32) [+ time-embedding add] [+ SiLU] on channels_last `[(b f), h, w, C]` fp16 activations, forward and input
+// gradient (sm_100a). Reference: InflatedGroupNorm + nonlinearity, models/resnet.py:21-29, :186-204; the transformer
+// input norms models/attention.py:61,105 and models/motion_module.py:112,145 — all through ATen's NCHW GroupNorm, which
+// on a channels_last activation costs a layout copy in, a layout copy before the next cuDNN conv and two passes of
+// its own. These kernels read NHWC directly.
+//
+// HBM-bound: forward = 2 reads + 1 write of the tensor (statistics pass, then apply; the second read is an L2 hit for
+// tensors under ~60 MB), backward = 2 x (x, dz) reads + 1 write. What bounds a streaming kernel like this on B200 is
+// bytes in flight, so:
+//   * thread -> (8-channel vector column v, pixel lane): every access is a 128-bit load / store, a warp covers
+//     contiguous 512 B runs, and per-channel coefficients live in registers (no per-element integer division);
+//   * the pixel loop is unrolled x4 with the loads issued first (4 x 16 B in flight per thread);
+//   * partial statistics are merged with Chan's formula (robust to |mean| >> std): pixel lanes -> channel -> group by
+//     warp shuffles; the LAST CTA of a frame (atomic ticket) folds the per-split partials into (mean, rstd), so the
+//     apply pass reads 2 floats per group instead of re-folding the partials in every CTA.
+// Workspace layout (device memory, caller-owned): [4096 B tickets | N*G*2 floats finalised | N*S*G*3 floats partial].
+// The ticket region must be zero on first use; every call leaves it zero again.
+#include <math.h>
+
+#include "mc_common.cuh"
+
+namespace mc {
+
+union GVec8 {
+  uint4 u;
+  __half h[8];
+};
+
+constexpr int kGnTicketBytes = 4096;  // one uint32 per frame: N <= 1024
+constexpr int kGnMaxSplits = 64;
+
+// Chan et al. merge of (n, mean, M2) partials
+__device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float meanb, float m2b) {
+  if (nb == 0.f) return;
+  const float nn = n + nb;
+  const float delta = meanb - mean;
+  const float w = nb / nn;
+  mean += delta * w;
+  m2 += m2b + delta * delta * n * w;
+  n = nn;
+}
+
+__device__ __forceinline__ float silu_fwd(float f) { return __fdividef(f, 1.f + __expf(-f)); }
+__device__ __forceinline__ float silu_grad(float y) {
+  const float s = __fdividef(1.f, 1.f + __expf(-y));
+  return s * (1.f + y * (1.f - s));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward, pass 1: statistics. grid (N, S); thread -> (vector column v = tid % V, pixel lane pl = tid / V).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) groupnorm_stats_kernel(const __half* __restrict__ x,
+                                                              const __half* __restrict__ chan_bias, int frames_per_row,
+                                                              float* __restrict__ partial, float* __restrict__ stats,
+                                                              unsigned* __restrict__ tickets, int HW, int C, int G, int S,
+                                                              int lanes, float eps) {
+  extern __shared__ float sm[];
+  __shared__ unsigned s_ticket;
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int V = C / 8;
+  float* s_n = sm;               // [NT * 8] per (thread, channel-of-vector)
+  float* s_mean = sm + NT * 8;
+  float* s_m2 = sm + 2 * NT * 8;
+  float* c_n = sm + 3 * NT * 8;  // [C] per channel
+  float* c_mean = c_n + C;
+  float* c_m2 = c_mean + C;
+  const int n = blockIdx.x, s = blockIdx.y;
+  const int v = tid % V, pl = tid / V;
+  const bool active = pl < lanes;
+  const int p_begin = (int)(((int64_t)HW * s) / S), p_end = (int)(((int64_t)HW * (s + 1)) / S);
+
+  float sum[8], sq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+  float cnt = 0.f;
+  if (active) {
+    const __half* base = x + (int64_t)n * HW * C + v * 8;
+    GVec8 cb;
+    cb.u = make_uint4(0u, 0u, 0u, 0u);
+    const bool has_cb = chan_bias != nullptr;
+    if (has_cb) cb.u = *reinterpret_cast<const uint4*>(chan_bias + (int64_t)(n / frames_per_row) * C + v * 8);
+    auto acc = [&](const GVec8& a) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float f = __half2float(a.h[j]);
+        if (has_cb) f = round_half(f + __half2float(cb.h[j]));  // the eager `h + temb` is an fp16 tensor
+        sum[j] += f;
+        sq[j] = fmaf(f, f, sq[j]);
+      }
+    };
+    int p = p_begin + pl;
+    for (; p + 3 * lanes < p_end; p += 4 * lanes) {
+      GVec8 a0, a1, a2, a3;
+      a0.u = *reinterpret_cast<const uint4*>(base + (int64_t)p * C);
+      a1.u = *reinterpret_cast<const uint4*>(base + (int64_t)(p + lanes) * C);
+      a2.u = *reinterpret_cast<const uint4*>(base + (int64_t)(p + 2 * lanes) * C);
+      a3.u = *reinterpret_cast<const uint4*>(base + (int64_t)(p + 3 * lanes) * C);
+      acc(a0), acc(a1), acc(a2), acc(a3);
+      cnt += 4.f;
+    }
+    for (; p < p_end; p += lanes) {
+      GVec8 a;
+      a.u = *reinterpret_cast<const uint4*>(base + (int64_t)p * C);
+      acc(a);
+      cnt += 1.f;
+    }
+  }
+  // per thread (a few dozen samples per channel: fp32 sum / sum-of-squares is safe) -> (n, mean, M2)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float mean = cnt > 0.f ? sum[j] / cnt : 0.f;
+    const int slot = tid * 8 + j;
+    s_n[slot] = active ? cnt : 0.f;
+    s_mean[slot] = mean;
+    s_m2[slot] = cnt > 0.f ? fmaxf(sq[j] - sum[j] * mean, 0.f) : 0.f;
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += NT) {  // pixel lanes -> channel
+    const int vv = c >> 3, jj = c & 7;
+    float an = 0.f, amean = 0.f, am2 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      const int slot = (l * V + vv) * 8 + jj;
+      chan_merge(an, amean, am2, s_n[slot], s_mean[slot], s_m2[slot]);
+    }
+    c_n[c] = an, c_mean[c] = amean, c_m2[c] = am2;
+  }
+  __syncthreads();
+  const int cg = C / G, warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
+  for (int g = warp; g < G; g += nwarps) {  // channels -> group: one warp per group
+    float an = 0.f, amean = 0.f, am2 = 0.f;
+    for (int c = g * cg + lane; c < (g + 1) * cg; c += 32) chan_merge(an, amean, am2, c_n[c], c_mean[c], c_m2[c]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float bn = __shfl_xor_sync(0xffffffffu, an, off);
+      const float bmean = __shfl_xor_sync(0xffffffffu, amean, off);
+      const float bm2 = __shfl_xor_sync(0xffffffffu, am2, off);
+      chan_merge(an, amean, am2, bn, bmean, bm2);
+    }
+    if (lane == 0) {
+      float* out = partial + (((int64_t)n * S + s) * G + g) * 3;
+      out[0] = an, out[1] = amean, out[2] = am2;
+    }
+  }
+  // ---- the last CTA of frame n folds the S partials into (mean, rstd) ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(&tickets[n], 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)(S - 1)) return;
+  __threadfence();
+  const int slices = (NT / G) > 0 ? (NT / G) : 1;
+  for (int idx = tid; idx < G * slices; idx += NT) {
+    const int g = idx % G, k = idx / G;
+    float an = 0.f, amean = 0.f, am2 = 0.f;
+    for (int s2 = k; s2 < S; s2 += slices) {
+      const float* p = partial + (((int64_t)n * S + s2) * G + g) * 3;
+      chan_merge(an, amean, am2, __ldcg(p), __ldcg(p + 1), __ldcg(p + 2));
+    }
+    s_n[idx] = an, s_mean[idx] = amean, s_m2[idx] = am2;
+  }
+  __syncthreads();
+  for (int g = tid; g < G; g += NT) {
+    float an = 0.f, amean = 0.f, am2 = 0.f;
+    for (int k = 0; k < slices; ++k) chan_merge(an, amean, am2, s_n[k * G + g], s_mean[k * G + g], s_m2[k * G + g]);
+    stats[((int64_t)n * G + g) * 2] = amean;
+    stats[((int64_t)n * G + g) * 2 + 1] = rsqrtf(am2 / an + eps);
+  }
+  if (tid == 0) tickets[n] = 0u;
+}
+
+// forward, pass 2: y = a[c] * x + b[c] with a = rstd * gamma, b = beta - mean * a (ATen's fused-parameter form) [-> SiLU]
+template <bool SILU>
+__global__ void __launch_bounds__(512) groupnorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                              const __half* __restrict__ chan_bias, int frames_per_row,
+                                                              const float* __restrict__ stats,
+                                                              const __half* __restrict__ gamma,
+                                                              const __half* __restrict__ beta, int HW, int C, int G, int S,
+                                                              int lanes) {
+  const int tid = threadIdx.x, V = C / 8;
+  const int n = blockIdx.x, s = blockIdx.y;
+  const int v = tid % V, pl = tid / V;
+  if (pl >= lanes) return;
+  const int c0 = v * 8, cg = C / G;
+  float a[8], b[8];
+  GVec8 w, bt, cb;
+  w.u = *reinterpret_cast<const uint4*>(gamma + c0);
+  bt.u = *reinterpret_cast<const uint4*>(beta + c0);
+  cb.u = make_uint4(0u, 0u, 0u, 0u);
+  const bool has_cb = chan_bias != nullptr;
+  if (has_cb) cb.u = *reinterpret_cast<const uint4*>(chan_bias + (int64_t)(n / frames_per_row) * C + c0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cg;
+    const float mean = stats[((int64_t)n * G + g) * 2], rstd = stats[((int64_t)n * G + g) * 2 + 1];
+    a[j] = rstd * __half2float(w.h[j]);
+    b[j] = fmaf(-mean, a[j], __half2float(bt.h[j]));
+  }
+  const int p_begin = (int)(((int64_t)HW * s) / S), p_end = (int)(((int64_t)HW * (s + 1)) / S);
+  const __half* xb = x + (int64_t)n * HW * C + c0;
+  __half* yb = y + (int64_t)n * HW * C + c0;
+  auto norm = [&](const GVec8& in) {
+    GVec8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float xv = __half2float(in.h[j]);
+      if (has_cb) xv = round_half(xv + __half2float(cb.h[j]));
+      float f = fmaf(xv, a[j], b[j]);
+      if (SILU) f = silu_fwd(round_half(f));  // ATen rounds the GroupNorm output to fp16 before the separate SiLU kernel
+      o.h[j] = __float2half_rn(f);
+    }
+    return o;
+  };
+  int p = p_begin + pl;
+  for (; p + 3 * lanes < p_end; p += 4 * lanes) {
+    GVec8 a0, a1, a2, a3;
+    a0.u = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
+    a1.u = *reinterpret_cast<const uint4*>(xb + (int64_t)(p + lanes) * C);
+    a2.u = *reinterpret_cast<const uint4*>(xb + (int64_t)(p + 2 * lanes) * C);
+    a3.u = *reinterpret_cast<const uint4*>(xb + (int64_t)(p + 3 * lanes) * C);
+    *reinterpret_cast<uint4*>(yb + (int64_t)p * C) = norm(a0).u;
+    *reinterpret_cast<uint4*>(yb + (int64_t)(p + lanes) * C) = norm(a1).u;
+    *reinterpret_cast<uint4*>(yb + (int64_t)(p + 2 * lanes) * C) = norm(a2).u;
+    *reinterpret_cast<uint4*>(yb + (int64_t)(p + 3 * lanes) * C) = norm(a3).u;
+  }
+  for (; p < p_end; p += lanes) {
+    GVec8 a0;
+    a0.u = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
+    *reinterpret_cast<uint4*>(yb + (int64_t)p * C) = norm(a0).u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward (input gradient; weights are frozen on this path, t2v_video_sample.py:67-68)
+//   dxhat = dy * gamma, dy = dz * silu'(y) when SiLU was fused;  A = mean_group(dxhat), B = mean_group(dxhat * xhat)
+//   dx = rstd * (dxhat - A - xhat * B)
+// pass 1: per (frame, split) partial sums of dxhat and dxhat * xhat per group; last CTA of the frame -> (A, B)
+// ---------------------------------------------------------------------------------------------------------------
+struct GnBwdCoef {
+  float mean[8], rstd[8], w[8], b[8];
+};
+
+__device__ __forceinline__ void gn_bwd_coef(GnBwdCoef& k, const float* __restrict__ stats, const __half* __restrict__ gamma,
+                                            const __half* __restrict__ beta, int n, int c0, int cg, int G) {
+  GVec8 w, b;
+  w.u = *reinterpret_cast<const uint4*>(gamma + c0);
+  b.u = *reinterpret_cast<const uint4*>(beta + c0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cg;
+    k.mean[j] = stats[((int64_t)n * G + g) * 2];
+    k.rstd[j] = stats[((int64_t)n * G + g) * 2 + 1];
+    k.w[j] = __half2float(w.h[j]);
+    k.b[j] = __half2float(b.h[j]);
+  }
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(512) groupnorm_bwd_reduce_kernel(
+    const __half* __restrict__ x, const __half* __restrict__ chan_bias, int frames_per_row, const __half* __restrict__ dz,
+    const float* __restrict__ stats, const __half* __restrict__ gamma, const __half* __restrict__ beta,
+    float* __restrict__ partial, float* __restrict__ ab, unsigned* __restrict__ tickets, int HW, int C, int G, int S,
+    int lanes) {
+  extern __shared__ float sm[];
+  __shared__ unsigned s_ticket;
+  const int NT = blockDim.x, tid = threadIdx.x, V = C / 8;
+  float* s_a = sm;  // [NT * 8]
+  float* s_b = sm + NT * 8;
+  float* c_a = sm + 2 * NT * 8;  // [C]
+  float* c_b = c_a + C;
+  const int n = blockIdx.x, s = blockIdx.y;
+  const int v = tid % V, pl = tid / V, cg = C / G;
+  const bool active = pl < lanes;
+  const int p_begin = (int)(((int64_t)HW * s) / S), p_end = (int)(((int64_t)HW * (s + 1)) / S);
+  float sa[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sa[j] = sb[j] = 0.f;
+  if (active) {
+    const int c0 = v * 8;
+    GnBwdCoef k;
+    gn_bwd_coef(k, stats, gamma, beta, n, c0, cg, G);
+    GVec8 cb;
+    cb.u = make_uint4(0u, 0u, 0u, 0u);
+    const bool has_cb = chan_bias != nullptr;
+    if (has_cb) cb.u = *reinterpret_cast<const uint4*>(chan_bias + (int64_t)(n / frames_per_row) * C + c0);
+    const __half* xb = x + (int64_t)n * HW * C + c0;
+    const __half* db = dz + (int64_t)n * HW * C + c0;
+    auto acc = [&](const GVec8& a, const GVec8& d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float xv = __half2float(a.h[j]);
+        if (has_cb) xv = round_half(xv + __half2float(cb.h[j]));
+        const float xh = (xv - k.mean[j]) * k.rstd[j];
+        float dy = __half2float(d.h[j]);
+        if (SILU) dy *= silu_grad(round_half(fmaf(xh, k.w[j], k.b[j])));
+        const float dxh = dy * k.w[j];
+        sa[j] += dxh;
+        sb[j] = fmaf(dxh, xh, sb[j]);
+      }
+    };
+    int p = p_begin + pl;
+    for (; p + lanes < p_end; p += 2 * lanes) {
+      GVec8 a0, a1, d0, d1;
+      a0.u = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
+      d0.u = *reinterpret_cast<const uint4*>(db + (int64_t)p * C);
+      a1.u = *reinterpret_cast<const uint4*>(xb + (int64_t)(p + lanes) * C);
+      d1.u = *reinterpret_cast<const uint4*>(db + (int64_t)(p + lanes) * C);
+      acc(a0, d0), acc(a1, d1);
+    }
+    for (; p < p_end; p += lanes) {
+      GVec8 a0, d0;
+      a0.u = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
+      d0.u = *reinterpret_cast<const uint4*>(db + (int64_t)p * C);
+      acc(a0, d0);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_a[tid * 8 + j] = active ? sa[j] : 0.f;
+    s_b[tid * 8 + j] = active ? sb[j] : 0.f;
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += NT) {
+    const int vv = c >> 3, jj = c & 7;
+    float ta = 0.f, tb = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      ta += s_a[(l * V + vv) * 8 + jj];
+      tb += s_b[(l * V + vv) * 8 + jj];
+    }
+    c_a[c] = ta, c_b[c] = tb;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
+  for (int g = warp; g < G; g += nwarps) {
+    float ta = 0.f, tb = 0.f;
+    for (int c = g * cg + lane; c < (g + 1) * cg; c += 32) ta += c_a[c], tb += c_b[c];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      ta += __shfl_xor_sync(0xffffffffu, ta, off);
+      tb += __shfl_xor_sync(0xffffffffu, tb, off);
+    }
+    if (lane == 0) {
+      float* out = partial + (((int64_t)n * S + s) * G + g) * 2;
+      out[0] = ta, out[1] = tb;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(&tickets[n], 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)(S - 1)) return;
+  __threadfence();
+  const float inv_m = 1.f / ((float)HW * (float)cg);
+  for (int g = tid; g < G; g += NT) {
+    float ta = 0.f, tb = 0.f;
+    for (int s2 = 0; s2 < S; ++s2) {  // fixed order: deterministic
+      const float* p = partial + (((int64_t)n * S + s2) * G + g) * 2;
+      ta += __ldcg(p), tb += __ldcg(p + 1);
+    }
+    ab[((int64_t)n * G + g) * 2] = ta * inv_m;
+    ab[((int64_t)n * G + g) * 2 + 1] = tb * inv_m;
+  }
+  if (tid == 0) tickets[n] = 0u;
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(512) groupnorm_bwd_apply_kernel(
+    const __half* __restrict__ x, const __half* __restrict__ chan_bias, int frames_per_row, const __half* __restrict__ dz,
+    __half* __restrict__ dx, const float* __restrict__ stats, const float* __restrict__ ab, const __half* __restrict__ gamma,
+    const __half* __restrict__ beta, int HW, int C, int G, int S, int lanes) {
+  const int tid = threadIdx.x, V = C / 8;
+  const int n = blockIdx.x, s = blockIdx.y;
+  const int v = tid % V, pl = tid / V;
+  if (pl >= lanes) return;
+  const int c0 = v * 8, cg = C / G;
+  GnBwdCoef k;
+  gn_bwd_coef(k, stats, gamma, beta, n, c0, cg, G);
+  float ga[8], gb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cg;
+    ga[j] = ab[((int64_t)n * G + g) * 2];
+    gb[j] = ab[((int64_t)n * G + g) * 2 + 1];
+  }
+  GVec8 cb;
+  cb.u = make_uint4(0u, 0u, 0u, 0u);
+  const bool has_cb = chan_bias != nullptr;
+  if (has_cb) cb.u = *reinterpret_cast<const uint4*>(chan_bias + (int64_t)(n / frames_per_row) * C + c0);
+  const int p_begin = (int)(((int64_t)HW * s) / S), p_end = (int)(((int64_t)HW * (s + 1)) / S);
+  const __half* xb = x + (int64_t)n * HW * C + c0;
+  const __half* db = dz + (int64_t)n * HW * C + c0;
+  __half* ob = dx + (int64_t)n * HW * C + c0;
+  auto grad = [&](const GVec8& a, const GVec8& d) {
+    GVec8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float xv = __half2float(a.h[j]);
+      if (has_cb) xv = round_half(xv + __half2float(cb.h[j]));
+      const float xh = (xv - k.mean[j]) * k.rstd[j];
+      float dy = __half2float(d.h[j]);
+      if (SILU) dy *= silu_grad(round_half(fmaf(xh, k.w[j], k.b[j])));
+      const float dxh = dy * k.w[j];
+      o.h[j] = __float2half_rn(k.rstd[j] * (dxh - ga[j] - xh * gb[j]));
+    }
+    return o;
+  };
+  int p = p_begin + pl;
+  for (; p + lanes < p_end; p += 2 * lanes) {
+    GVec8 a0, a1, d0, d1;
+    a0.u = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
+    d0.u = *reinterpret_cast<const uint4*>(db + (int64_t)p * C);
+    a1.u = *reinterpret_cast<const uint4*>(xb + (int64_t)(p + lanes) * C);
+    d1.u = *reinterpret_cast<const uint4*>(db + (int64_t)(p + lanes) * C);
+    *reinterpret_cast<uint4*>(ob + (int64_t)p * C) = grad(a0, d0).u;
+    *reinterpret_cast<uint4*>(ob + (int64_t)(p + lanes) * C) = grad(a1, d1).u;
+  }
+  for (; p < p_end; p += lanes) {
+    GVec8 a0, d0;
+    a0.u = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
+    d0.u = *reinterpret_cast<const uint4*>(db + (int64_t)p * C);
+    *reinterpret_cast<uint4*>(ob + (int64_t)p * C) = grad(a0, d0).u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+struct GnLaunch {
+  int V, lanes, NT;
+};
+
+static GnLaunch gn_launch(int C) {
+  GnLaunch g;
+  g.V = C / 8;
+  g.lanes = 256 / g.V;
+  if (g.lanes < 1) g.lanes = 1;
+  if (g.V * g.lanes < 192 && g.V * (g.lanes + 1) <= 512) ++g.lanes;  // e.g. C = 1280: 2 pixel lanes, 320 threads
+  g.NT = (g.V * g.lanes + 31) / 32 * 32;
+  return g;
+}
+
+// splits of a frame's pixels: `ctas` CTAs over the machine, at least `min_px` pixels per pixel lane and split
+static int gn_splits(int N, int HW, int lanes, int ctas, int min_px) {
+  int S = (ctas + N - 1) / N;
+  const int cap = HW / (lanes * min_px);
+  if (S > cap) S = cap;
+  if (S > kGnMaxSplits) S = kGnMaxSplits;
+  if (S < 1) S = 1;
+  return S;
+}
+
+static int gn_check(const char* what, int N, int HW, int C, int G) {
+  if (N <= 0 || HW <= 0) {
+    set_error("%s: non-positive dims", what);
+    return MC_E_INVALID;
+  }
+  if (C % 8 != 0 || C % G != 0 || C > 4096 || G > 256 || N > kGnTicketBytes / 4) {
+    set_error("%s: need C %% 8 == 0, C %% G == 0, C <= 4096, G <= 256, N <= 1024 (got N=%d C=%d G=%d)", what, N, C, G);
+    return MC_E_UNSUPPORTED;
+  }
+  return MC_OK;
+}
+
+struct GnWorkspace {
+  unsigned* tickets;
+  float* finalised;  // fwd: (mean, rstd); bwd: (A/m, B/m)   [N, G, 2]
+  float* partial;
+};
+
+static GnWorkspace gn_workspace(void* ws, int N, int G) {
+  GnWorkspace w;
+  w.tickets = reinterpret_cast<unsigned*>(ws);
+  w.finalised = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kGnTicketBytes);
+  w.partial = w.finalised + (int64_t)N * G * 2;
+  return w;
+}
+
+}  // namespace mc
+
+extern "C" int64_t mc_groupnorm_workspace_bytes(int N, int G) {
+  return mc::kGnTicketBytes + (int64_t)N * G * 2 * sizeof(float) + (int64_t)N * mc::kGnMaxSplits * G * 3 * sizeof(float);
+}
+
+extern "C" int mc_groupnorm_nhwc(const void* x, const void* chan_bias, int frames_per_bias_row, void* y,
+                                 const void* gamma, const void* beta, void* workspace, int64_t workspace_bytes, int N,
+                                 int HW, int C, int G, float eps, int fuse_silu, void* stream) {
+  using namespace mc;
+  if (!x || !y || !gamma || !beta || !workspace) {
+    set_error("groupnorm_nhwc: null pointer");
+    return MC_E_INVALID;
+  }
+  int rc = gn_check("groupnorm_nhwc", N, HW, C, G);
+  if (rc != MC_OK) return rc;
+  if (chan_bias != nullptr && frames_per_bias_row <= 0) {
+    set_error("groupnorm_nhwc: frames_per_bias_row must be positive when chan_bias is given");
+    return MC_E_INVALID;
+  }
+  if (workspace_bytes < mc_groupnorm_workspace_bytes(N, G)) {
+    set_error("groupnorm_nhwc: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes,
+              (long long)mc_groupnorm_workspace_bytes(N, G));
+    return MC_E_INVALID;
+  }
+  const GnLaunch L = gn_launch(C);
+  const GnWorkspace w = gn_workspace(workspace, N, G);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S1 = gn_splits(N, HW, L.lanes, 148 * 4, 8);
+  const int smem1 = (3 * L.NT * 8 + 3 * C) * (int)sizeof(float);
+  if (smem1 > 48 * 1024)
+    cudaFuncSetAttribute(groupnorm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+  groupnorm_stats_kernel<<<dim3(N, S1), L.NT, smem1, st>>>((const __half*)x, (const __half*)chan_bias,
+                                                           frames_per_bias_row, w.partial, w.finalised, w.tickets, HW, C, G,
+                                                           S1, L.lanes, eps);
+  count_launch();
+  rc = check_launch("groupnorm_stats");
+  if (rc != MC_OK) return rc;
+  const int S2 = gn_splits(N, HW, L.lanes, 148 * 6, 4);
+  if (fuse_silu)
+    groupnorm_apply_kernel<true><<<dim3(N, S2), L.NT, 0, st>>>((const __half*)x, (__half*)y, (const __half*)chan_bias,
+                                                               frames_per_bias_row, w.finalised, (const __half*)gamma,
+                                                               (const __half*)beta, HW, C, G, S2, L.lanes);
+  else
+    groupnorm_apply_kernel<false><<<dim3(N, S2), L.NT, 0, st>>>((const __half*)x, (__half*)y, (const __half*)chan_bias,
+                                                                frames_per_bias_row, w.finalised, (const __half*)gamma,
+                                                                (const __half*)beta, HW, C, G, S2, L.lanes);
+  count_launch();
+  return check_launch("groupnorm_apply");
+}
+
+extern "C" int mc_groupnorm_nhwc_stats(const void* workspace, void* stats, int N, int HW, int G, float eps, void* stream) {
+  using namespace mc;
+  (void)HW, (void)eps;  // kept in the signature: the statistics are final once mc_groupnorm_nhwc has run
+  if (!workspace || !stats || N <= 0 || G <= 0) {
+    set_error("groupnorm_nhwc_stats: null pointer or non-positive dims");
+    return MC_E_INVALID;
+  }
+  const GnWorkspace w = gn_workspace(const_cast<void*>(workspace), N, G);
+  const cudaError_t e = cudaMemcpyAsync(stats, w.finalised, (size_t)N * G * 2 * sizeof(float), cudaMemcpyDeviceToDevice,
+                                        (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_error("groupnorm_nhwc_stats: %s", cudaGetErrorString(e));
+    return MC_E_CUDA;
+  }
+  return MC_OK;
+}
+
+extern "C" int mc_groupnorm_nhwc_bwd(const void* x, const void* chan_bias, int frames_per_bias_row, const void* dz,
+                                     void* dx, const void* stats, const void* gamma, const void* beta, void* workspace,
+                                     int64_t workspace_bytes, int N, int HW, int C, int G, int fuse_silu, void* stream) {
+  using namespace mc;
+  if (!x || !dz || !dx || !stats || !gamma || !beta || !workspace) {
+    set_error("groupnorm_nhwc_bwd: null pointer");
+    return MC_E_INVALID;
+  }
+  int rc = gn_check("groupnorm_nhwc_bwd", N, HW, C, G);
+  if (rc != MC_OK) return rc;
+  if (chan_bias != nullptr && frames_per_bias_row <= 0) {
+    set_error("groupnorm_nhwc_bwd: frames_per_bias_row must be positive when chan_bias is given");
+    return MC_E_INVALID;
+  }
+  if (workspace_bytes < mc_groupnorm_workspace_bytes(N, G)) {
+    set_error("groupnorm_nhwc_bwd: workspace too small");
+    return MC_E_INVALID;
+  }
+  const GnLaunch L = gn_launch(C);
+  const GnWorkspace w = gn_workspace(workspace, N, G);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S1 = gn_splits(N, HW, L.lanes, 148 * 4, 4);
+  const int smem1 = (2 * L.NT * 8 + 2 * C) * (int)sizeof(float);
+  const __half *xp = (const __half*)x, *cbp = (const __half*)chan_bias, *dzp = (const __half*)dz;
+  const __half *gp = (const __half*)gamma, *bp = (const __half*)beta;
+  if (fuse_silu) {
+    if (smem1 > 48 * 1024)
+      cudaFuncSetAttribute(groupnorm_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    groupnorm_bwd_reduce_kernel<true><<<dim3(N, S1), L.NT, smem1, st>>>(xp, cbp, frames_per_bias_row, dzp,
+                                                                        (const float*)stats, gp, bp, w.partial, w.finalised,
+                                                                        w.tickets, HW, C, G, S1, L.lanes);
+  } else {
+    if (smem1 > 48 * 1024)
+      cudaFuncSetAttribute(groupnorm_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    groupnorm_bwd_reduce_kernel<false><<<dim3(N, S1), L.NT, smem1, st>>>(xp, cbp, frames_per_bias_row, dzp,
+                                                                         (const float*)stats, gp, bp, w.partial,
+                                                                         w.finalised, w.tickets, HW, C, G, S1, L.lanes);
+  }
+  count_launch();
+  rc = check_launch("groupnorm_bwd_reduce");
+  if (rc != MC_OK) return rc;
+  const int S2 = gn_splits(N, HW, L.lanes, 148 * 6, 2);
+  if (fuse_silu)
+    groupnorm_bwd_apply_kernel<true><<<dim3(N, S2), L.NT, 0, st>>>(xp, cbp, frames_per_bias_row, dzp, (__half*)dx,
+                                                                   (const float*)stats, w.finalised, gp, bp, HW, C, G, S2,
+                                                                   L.lanes);
+  else
+    groupnorm_bwd_apply_kernel<false><<<dim3(N, S2), L.NT, 0, st>>>(xp, cbp, frames_per_bias_row, dzp, (__half*)dx,
+                                                                    (const float*)stats, w.finalised, gp, bp, HW, C, G, S2,
+                                                                    L.lanes);
+  count_launch();
+  return check_launch("groupnorm_bwd_apply");
+}

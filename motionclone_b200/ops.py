@@ -323,11 +323,14 @@ def glue_kernels_ok(x: Tensor) -> bool:
     return x.is_cuda and x.dtype == torch.float16
 
 
-def _workspace(x: Tensor, need: int) -> Tensor:
-    key = (x.device, torch.cuda.current_stream().cuda_stream)
+def _workspace(x: Tensor, need: int, role: str = "fwd") -> Tensor:
+    """Per (device, stream, role) scratch for the GroupNorm kernels. Zero-initialised: its first 4 KB are the per-frame
+    tickets of the last-CTA reduction, which the kernels leave at zero (include/motionclone_b200.h). Forward and backward
+    use different buffers (the forward's finalised statistics are copied out for the backward)."""
+    key = (x.device, torch.cuda.current_stream().cuda_stream, role)
     ws = _gn_workspace.get(key)
     if ws is None or ws.numel() < need:
-        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=x.device)
+        ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=x.device)
         _gn_workspace[key] = ws
     return ws
 
@@ -382,7 +385,7 @@ class GroupNormNHWCFn(torch.autograd.Function):
         chan_bias, fpr = _check_chan_bias(x, chan_bias)
         N, C, H, W = x.shape
         dx = torch.empty_like(x)
-        ws = _workspace(x, N * 64 * ctx.groups * 8)
+        ws = _workspace(x, int(_lib.lib().mc_groupnorm_workspace_bytes(N, ctx.groups)), "bwd")
         st = _lib.lib().mc_groupnorm_nhwc_bwd(_ptr(x), _ptr(chan_bias), fpr, _ptr(dz), _ptr(dx), _ptr(stats), _ptr(weight),
                                               _ptr(bias), _ptr(ws), ws.numel(), N, H * W, C, ctx.groups, int(ctx.silu),
                                               _stream())
@@ -547,3 +550,27 @@ class CrossAttentionTC(torch.autograd.Function):
                                       "(frozen projections of a constant prompt embedding)")
         q, k, v = ctx.saved_tensors
         return cross_attention_backward(q, k, v, d_o, ctx.heads, ctx.scale), None, None, None, None
+
+
+SELF_ATTN_SHORT_MAX_TOKENS = 256
+SELF_ATTN_SHORT_HEAD_DIMS = (40, 64, 80, 160)
+
+
+def self_attention_short(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float) -> Tensor:
+    """tcgen05 spatial self-attention for N <= 256 tokens per frame (csrc/self_attn_tc.cu): q, k, v [B, N, C] views
+    with identical strides (column blocks of a fused QKV projection) -> o [B, N, C] contiguous. Inference passes only."""
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        _require(t, name)
+        if t.dim() != 3 or t.stride(2) != 1:
+            raise ValueError(f"{name} must be [B, N, C] with contiguous channels")
+        if t.shape != q.shape or t.stride() != q.stride():
+            raise ValueError("q, k, v must share shape and strides")
+    B, N, C = q.shape
+    o = torch.empty((B, N, C), dtype=q.dtype, device=q.device)
+    ev0 = TIMER.start() if TIMER is not None else None
+    st = _lib.lib().mc_self_attn_short_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), B, N, heads, C // heads, q.stride(0),
+                                           q.stride(1), o.stride(0), o.stride(1), float(scale), _stream())
+    _lib.check(st, "mc_self_attn_short_fwd")
+    if ev0 is not None:  # Q, K, V read + O written
+        TIMER.stop("self_attn_short_fwd", 4 * B * N * C * 2, ev0)
+    return o

@@ -18,6 +18,7 @@ Design differences (B200-first):
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -28,6 +29,8 @@ from . import ops
 
 
 _XATTN_TC_HEAD_DIMS = (16, 32, 40, 64, 80, 160)  # instantiations of csrc/cross_attn_tc.cu
+# feed-forward row blocking (bytes of [rows, 8C] projection per block; 0 disables): see FeedForward._forward_l2_blocked
+_FF_CHUNK_BYTES = int(float(os.environ.get("MC_FF_CHUNK_MB", "32")) * (1 << 20))
 
 
 def _frozen(*params) -> bool:
@@ -100,9 +103,30 @@ class FeedForward(nn.Module):
         self.net = nn.ModuleList([GEGLU(dim, inner), nn.Dropout(dropout), nn.Linear(inner, dim_out or dim)])
 
     def forward(self, x):
+        if _FF_CHUNK_BYTES > 0 and ops.glue_kernels_ok(x) and not (torch.is_grad_enabled() and x.requires_grad) \
+                and x.is_contiguous():
+            proj, lin = self.net[0].proj, self.net[2]
+            rows = x.numel() // x.shape[-1]
+            rows_per_chunk = max(256, (_FF_CHUNK_BYTES // (2 * proj.out_features)) // 256 * 256)
+            if rows > rows_per_chunk + rows_per_chunk // 2 and proj.out_features % 16 == 0 and lin.bias is not None:
+                return self._forward_l2_blocked(x, rows, rows_per_chunk)
         for m in self.net:
             x = m(x)
         return x
+
+    def _forward_l2_blocked(self, x, rows: int, rows_per_chunk: int):
+        """Inference passes: project -> GEGLU -> project back one row block at a time, sized so the [rows, 8C] projection
+        (the largest intermediate of the UNet: 335 MB at C = 320, 16 frames) is consumed by the GEGLU kernel while it is
+        still in the 126 MB L2, instead of making a round trip through HBM. Same arithmetic, same rounding points."""
+        proj, lin = self.net[0].proj, self.net[2]
+        x2 = x.view(rows, x.shape[-1])
+        out = torch.empty((rows, lin.out_features), dtype=x.dtype, device=x.device)
+        w2t = lin.weight.t()
+        for r0 in range(0, rows, rows_per_chunk):
+            r1 = min(rows, r0 + rows_per_chunk)
+            g = ops.geglu(F.linear(x2[r0:r1], proj.weight, proj.bias))
+            torch.addmm(lin.bias, g, w2t, out=out[r0:r1])
+        return out.view(*x.shape[:-1], lin.out_features)
 
 
 class CrossAttention(nn.Module):
@@ -209,8 +233,15 @@ class CrossAttention(nn.Module):
             if self.processor is not None:
                 self.processor.record_qkv(self, hidden_states, qkv[:, :, 0].reshape(bf, n, inner),
                                           qkv[:, :, 1].reshape(bf, n, inner), qkv[:, :, 2].reshape(bf, n, inner), None)
-            o = F.scaled_dot_product_attention(q, k, v, scale=self.scale)  # library flash kernel at the xformers seam
-            o = o.transpose(1, 2).reshape(bf, n, inner)
+            if n <= ops.SELF_ATTN_SHORT_MAX_TOKENS and dh in ops.SELF_ATTN_SHORT_HEAD_DIMS and ops.glue_kernels_ok(qkv) \
+                    and not (torch.is_grad_enabled() and qkv.requires_grad):
+                # 16x16 / 8x8 latent levels, inference passes: whole key axis in one TMEM tile (csrc/self_attn_tc.cu)
+                qkv3 = qkv.view(bf, n, 3 * inner)
+                o = ops.self_attention_short(qkv3[..., :inner], qkv3[..., inner:2 * inner], qkv3[..., 2 * inner:], h,
+                                             self.scale)
+            else:
+                o = F.scaled_dot_product_attention(q, k, v, scale=self.scale)  # library flash kernel at the xformers seam
+                o = o.transpose(1, 2).reshape(bf, n, inner)
         else:
             ctx = encoder_hidden_states
             b = ctx.shape[0]
