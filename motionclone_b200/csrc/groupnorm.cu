@@ -9,10 +9,13 @@
 // bytes in flight, so:
 //   * thread -> (8-channel vector column v, pixel lane): every access is a 128-bit load / store, a warp covers
 //     contiguous 512 B runs, and per-channel coefficients live in registers (no per-element integer division);
-//   * the pixel loop is unrolled x4 with the loads issued first (4 x 16 B in flight per thread);
-//   * partial statistics are merged with Chan's formula (robust to |mean| >> std): pixel lanes -> channel -> group by
-//     warp shuffles; the LAST CTA of a frame (atomic ticket) folds the per-split partials into (mean, rstd), so the
-//     apply pass reads 2 floats per group instead of re-folding the partials in every CTA.
+//   * a frame is cut into enough splits that a thread owns <= 8 pixels (4 in the backward: two tensors) and issues ALL
+//     its loads before touching the data (8 x 16 B in flight per thread, one DRAM latency per CTA instead of one per
+//     loop trip);
+//   * inside a CTA (<= a few hundred samples per group) plain fp32 sums / sums of squares are reduced with adds only
+//     (shared memory, then one warp per group with shuffles); ACROSS splits the (count, mean, M2) partials are merged
+//     with Chan's formula (robust to |mean| >> std) by the LAST CTA of the frame (atomic ticket), which writes
+//     (mean, rstd): the apply pass reads 2 floats per group instead of re-folding the partials in every CTA.
 // Workspace layout (device memory, caller-owned): [4096 B tickets | N*G*2 floats finalised | N*S*G*3 floats partial].
 // The ticket region must be zero on first use; every call leaves it zero again.
 #include <math.h>
@@ -27,7 +30,9 @@ union GVec8 {
 };
 
 constexpr int kGnTicketBytes = 4096;  // one uint32 per frame: N <= 1024
-constexpr int kGnMaxSplits = 64;
+constexpr int kGnMaxSplits = 128;
+constexpr int kGnPixFwd = 8;  // pixels per thread and trip (loads in flight): forward
+constexpr int kGnPixBwd = 4;  // backward (x and dz)
 
 // Chan et al. merge of (n, mean, M2) partials
 __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float meanb, float m2b) {
@@ -49,6 +54,23 @@ __device__ __forceinline__ float silu_grad(float y) {
 // ---------------------------------------------------------------------------------------------------------------
 // forward, pass 1: statistics. grid (N, S); thread -> (vector column v = tid % V, pixel lane pl = tid / V).
 // ---------------------------------------------------------------------------------------------------------------
+// sum over the (lanes x cg) per-(thread, channel) slots of group g held in shared memory; result valid in every lane
+__device__ __forceinline__ void gn_group_sum2(const float* __restrict__ s_a, const float* __restrict__ s_b, int g, int cg,
+                                              int lanes, int V, int lane, float& ta, float& tb) {
+  ta = tb = 0.f;
+  for (int k = lane; k < lanes * cg; k += 32) {
+    const int l = k / cg, c = g * cg + (k - l * cg);
+    const int slot = (l * V + (c >> 3)) * 8 + (c & 7);
+    ta += s_a[slot];
+    tb += s_b[slot];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    ta += __shfl_xor_sync(0xffffffffu, ta, off);
+    tb += __shfl_xor_sync(0xffffffffu, tb, off);
+  }
+}
+
 __global__ void __launch_bounds__(512) groupnorm_stats_kernel(const __half* __restrict__ x,
                                                               const __half* __restrict__ chan_bias, int frames_per_row,
                                                               float* __restrict__ partial, float* __restrict__ stats,
@@ -58,12 +80,8 @@ __global__ void __launch_bounds__(512) groupnorm_stats_kernel(const __half* __re
   __shared__ unsigned s_ticket;
   const int NT = blockDim.x, tid = threadIdx.x;
   const int V = C / 8;
-  float* s_n = sm;               // [NT * 8] per (thread, channel-of-vector)
-  float* s_mean = sm + NT * 8;
-  float* s_m2 = sm + 2 * NT * 8;
-  float* c_n = sm + 3 * NT * 8;  // [C] per channel
-  float* c_mean = c_n + C;
-  float* c_m2 = c_mean + C;
+  float* s_sum = sm;          // [NT * 8] per (thread, channel-of-vector)
+  float* s_sq = sm + NT * 8;
   const int n = blockIdx.x, s = blockIdx.y;
   const int v = tid % V, pl = tid / V;
   const bool active = pl < lanes;
@@ -72,82 +90,61 @@ __global__ void __launch_bounds__(512) groupnorm_stats_kernel(const __half* __re
   float sum[8], sq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
-  float cnt = 0.f;
   if (active) {
     const __half* base = x + (int64_t)n * HW * C + v * 8;
-    GVec8 cb;
-    cb.u = make_uint4(0u, 0u, 0u, 0u);
     const bool has_cb = chan_bias != nullptr;
-    if (has_cb) cb.u = *reinterpret_cast<const uint4*>(chan_bias + (int64_t)(n / frames_per_row) * C + v * 8);
-    auto acc = [&](const GVec8& a) {
+    for (int p = p_begin + pl; p < p_end; p += kGnPixFwd * lanes) {
+      GVec8 a[kGnPixFwd];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float f = __half2float(a.h[j]);
-        if (has_cb) f = round_half(f + __half2float(cb.h[j]));  // the eager `h + temb` is an fp16 tensor
-        sum[j] += f;
-        sq[j] = fmaf(f, f, sq[j]);
+      for (int u = 0; u < kGnPixFwd; ++u) {  // all loads first
+        const int pp = p + u * lanes;
+        a[u].u = make_uint4(0u, 0u, 0u, 0u);
+        if (pp < p_end) a[u].u = *reinterpret_cast<const uint4*>(base + (int64_t)pp * C);
       }
-    };
-    int p = p_begin + pl;
-    for (; p + 3 * lanes < p_end; p += 4 * lanes) {
-      GVec8 a0, a1, a2, a3;
-      a0.u = *reinterpret_cast<const uint4*>(base + (int64_t)p * C);
-      a1.u = *reinterpret_cast<const uint4*>(base + (int64_t)(p + lanes) * C);
-      a2.u = *reinterpret_cast<const uint4*>(base + (int64_t)(p + 2 * lanes) * C);
-      a3.u = *reinterpret_cast<const uint4*>(base + (int64_t)(p + 3 * lanes) * C);
-      acc(a0), acc(a1), acc(a2), acc(a3);
-      cnt += 4.f;
-    }
-    for (; p < p_end; p += lanes) {
-      GVec8 a;
-      a.u = *reinterpret_cast<const uint4*>(base + (int64_t)p * C);
-      acc(a);
-      cnt += 1.f;
+      GVec8 cb;
+      cb.u = make_uint4(0u, 0u, 0u, 0u);
+      if (has_cb) cb.u = *reinterpret_cast<const uint4*>(chan_bias + (int64_t)(n / frames_per_row) * C + v * 8);
+#pragma unroll
+      for (int u = 0; u < kGnPixFwd; ++u) {
+        if (p + u * lanes < p_end) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float f = __half2float(a[u].h[j]);
+            if (has_cb) f = round_half(f + __half2float(cb.h[j]));  // the eager `h + temb` is an fp16 tensor
+            sum[j] += f;
+            sq[j] = fmaf(f, f, sq[j]);
+          }
+        }
+      }
     }
   }
-  // per thread (a few dozen samples per channel: fp32 sum / sum-of-squares is safe) -> (n, mean, M2)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float mean = cnt > 0.f ? sum[j] / cnt : 0.f;
-    const int slot = tid * 8 + j;
-    s_n[slot] = active ? cnt : 0.f;
-    s_mean[slot] = mean;
-    s_m2[slot] = cnt > 0.f ? fmaxf(sq[j] - sum[j] * mean, 0.f) : 0.f;
-  }
-  __syncthreads();
-  for (int c = tid; c < C; c += NT) {  // pixel lanes -> channel
-    const int vv = c >> 3, jj = c & 7;
-    float an = 0.f, amean = 0.f, am2 = 0.f;
-    for (int l = 0; l < lanes; ++l) {
-      const int slot = (l * V + vv) * 8 + jj;
-      chan_merge(an, amean, am2, s_n[slot], s_mean[slot], s_m2[slot]);
-    }
-    c_n[c] = an, c_mean[c] = amean, c_m2[c] = am2;
+    s_sum[tid * 8 + j] = active ? sum[j] : 0.f;
+    s_sq[tid * 8 + j] = active ? sq[j] : 0.f;
   }
   __syncthreads();
   const int cg = C / G, warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
-  for (int g = warp; g < G; g += nwarps) {  // channels -> group: one warp per group
-    float an = 0.f, amean = 0.f, am2 = 0.f;
-    for (int c = g * cg + lane; c < (g + 1) * cg; c += 32) chan_merge(an, amean, am2, c_n[c], c_mean[c], c_m2[c]);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float bn = __shfl_xor_sync(0xffffffffu, an, off);
-      const float bmean = __shfl_xor_sync(0xffffffffu, amean, off);
-      const float bm2 = __shfl_xor_sync(0xffffffffu, am2, off);
-      chan_merge(an, amean, am2, bn, bmean, bm2);
-    }
+  const float cnt = (float)cg * (float)(p_end - p_begin);  // samples per group in this split
+  for (int g = warp; g < G; g += nwarps) {  // one warp per group: adds only
+    float ts, tq;
+    gn_group_sum2(s_sum, s_sq, g, cg, lanes, V, lane, ts, tq);
     if (lane == 0) {
+      const float mean = cnt > 0.f ? ts / cnt : 0.f;
       float* out = partial + (((int64_t)n * S + s) * G + g) * 3;
-      out[0] = an, out[1] = amean, out[2] = am2;
+      out[0] = cnt, out[1] = mean, out[2] = cnt > 0.f ? fmaxf(tq - ts * mean, 0.f) : 0.f;
     }
   }
-  // ---- the last CTA of frame n folds the S partials into (mean, rstd) ----
+  // ---- the last CTA of frame n folds the S partials into (mean, rstd) with Chan's formula ----
   __threadfence();
   __syncthreads();
   if (tid == 0) s_ticket = atomicAdd(&tickets[n], 1u);
   __syncthreads();
   if (s_ticket != (unsigned)(S - 1)) return;
   __threadfence();
+  float* f_n = sm;  // re-use of the (sum, sq) slots: three arrays of NT floats (slices * G <= NT)
+  float* f_mean = sm + NT;
+  float* f_m2 = sm + 2 * NT;
   const int slices = (NT / G) > 0 ? (NT / G) : 1;
   for (int idx = tid; idx < G * slices; idx += NT) {
     const int g = idx % G, k = idx / G;
@@ -156,12 +153,12 @@ __global__ void __launch_bounds__(512) groupnorm_stats_kernel(const __half* __re
       const float* p = partial + (((int64_t)n * S + s2) * G + g) * 3;
       chan_merge(an, amean, am2, __ldcg(p), __ldcg(p + 1), __ldcg(p + 2));
     }
-    s_n[idx] = an, s_mean[idx] = amean, s_m2[idx] = am2;
+    f_n[idx] = an, f_mean[idx] = amean, f_m2[idx] = am2;  // idx < G * slices <= NT (G <= 128 <= NT)
   }
   __syncthreads();
   for (int g = tid; g < G; g += NT) {
     float an = 0.f, amean = 0.f, am2 = 0.f;
-    for (int k = 0; k < slices; ++k) chan_merge(an, amean, am2, s_n[k * G + g], s_mean[k * G + g], s_m2[k * G + g]);
+    for (int k = 0; k < slices; ++k) chan_merge(an, amean, am2, f_n[k * G + g], f_mean[k * G + g], f_m2[k * G + g]);
     stats[((int64_t)n * G + g) * 2] = amean;
     stats[((int64_t)n * G + g) * 2 + 1] = rsqrtf(am2 / an + eps);
   }
@@ -181,6 +178,19 @@ __global__ void __launch_bounds__(512) groupnorm_apply_kernel(const __half* __re
   const int v = tid % V, pl = tid / V;
   if (pl >= lanes) return;
   const int c0 = v * 8, cg = C / G;
+  const int p_begin = (int)(((int64_t)HW * s) / S), p_end = (int)(((int64_t)HW * (s + 1)) / S);
+  const __half* xb = x + (int64_t)n * HW * C + c0;
+  __half* yb = y + (int64_t)n * HW * C + c0;
+  GVec8 in[kGnPixFwd];
+  auto load_batch = [&](int p) {
+#pragma unroll
+    for (int u = 0; u < kGnPixFwd; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p_end) in[u].u = *reinterpret_cast<const uint4*>(xb + (int64_t)pp * C);
+    }
+  };
+  int p = p_begin + pl;
+  if (p < p_end) load_batch(p);  // the tensor's loads go out before the (L2-resident) coefficient loads
   float a[8], b[8];
   GVec8 w, bt, cb;
   w.u = *reinterpret_cast<const uint4*>(gamma + c0);
@@ -195,14 +205,11 @@ __global__ void __launch_bounds__(512) groupnorm_apply_kernel(const __half* __re
     a[j] = rstd * __half2float(w.h[j]);
     b[j] = fmaf(-mean, a[j], __half2float(bt.h[j]));
   }
-  const int p_begin = (int)(((int64_t)HW * s) / S), p_end = (int)(((int64_t)HW * (s + 1)) / S);
-  const __half* xb = x + (int64_t)n * HW * C + c0;
-  __half* yb = y + (int64_t)n * HW * C + c0;
-  auto norm = [&](const GVec8& in) {
+  auto norm = [&](const GVec8& xin) {
     GVec8 o;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float xv = __half2float(in.h[j]);
+      float xv = __half2float(xin.h[j]);
       if (has_cb) xv = round_half(xv + __half2float(cb.h[j]));
       float f = fmaf(xv, a[j], b[j]);
       if (SILU) f = silu_fwd(round_half(f));  // ATen rounds the GroupNorm output to fp16 before the separate SiLU kernel
@@ -210,22 +217,14 @@ __global__ void __launch_bounds__(512) groupnorm_apply_kernel(const __half* __re
     }
     return o;
   };
-  int p = p_begin + pl;
-  for (; p + 3 * lanes < p_end; p += 4 * lanes) {
-    GVec8 a0, a1, a2, a3;
-    a0.u = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
-    a1.u = *reinterpret_cast<const uint4*>(xb + (int64_t)(p + lanes) * C);
-    a2.u = *reinterpret_cast<const uint4*>(xb + (int64_t)(p + 2 * lanes) * C);
-    a3.u = *reinterpret_cast<const uint4*>(xb + (int64_t)(p + 3 * lanes) * C);
-    *reinterpret_cast<uint4*>(yb + (int64_t)p * C) = norm(a0).u;
-    *reinterpret_cast<uint4*>(yb + (int64_t)(p + lanes) * C) = norm(a1).u;
-    *reinterpret_cast<uint4*>(yb + (int64_t)(p + 2 * lanes) * C) = norm(a2).u;
-    *reinterpret_cast<uint4*>(yb + (int64_t)(p + 3 * lanes) * C) = norm(a3).u;
-  }
-  for (; p < p_end; p += lanes) {
-    GVec8 a0;
-    a0.u = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
-    *reinterpret_cast<uint4*>(yb + (int64_t)p * C) = norm(a0).u;
+  while (p < p_end) {
+#pragma unroll
+    for (int u = 0; u < kGnPixFwd; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p_end) *reinterpret_cast<uint4*>(yb + (int64_t)pp * C) = norm(in[u]).u;
+    }
+    p += kGnPixFwd * lanes;
+    if (p < p_end) load_batch(p);
   }
 }
 
@@ -265,8 +264,6 @@ __global__ void __launch_bounds__(512) groupnorm_bwd_reduce_kernel(
   const int NT = blockDim.x, tid = threadIdx.x, V = C / 8;
   float* s_a = sm;  // [NT * 8]
   float* s_b = sm + NT * 8;
-  float* c_a = sm + 2 * NT * 8;  // [C]
-  float* c_b = c_a + C;
   const int n = blockIdx.x, s = blockIdx.y;
   const int v = tid % V, pl = tid / V, cg = C / G;
   const bool active = pl < lanes;
@@ -297,20 +294,19 @@ __global__ void __launch_bounds__(512) groupnorm_bwd_reduce_kernel(
         sb[j] = fmaf(dxh, xh, sb[j]);
       }
     };
-    int p = p_begin + pl;
-    for (; p + lanes < p_end; p += 2 * lanes) {
-      GVec8 a0, a1, d0, d1;
-      a0.u = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
-      d0.u = *reinterpret_cast<const uint4*>(db + (int64_t)p * C);
-      a1.u = *reinterpret_cast<const uint4*>(xb + (int64_t)(p + lanes) * C);
-      d1.u = *reinterpret_cast<const uint4*>(db + (int64_t)(p + lanes) * C);
-      acc(a0, d0), acc(a1, d1);
-    }
-    for (; p < p_end; p += lanes) {
-      GVec8 a0, d0;
-      a0.u = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
-      d0.u = *reinterpret_cast<const uint4*>(db + (int64_t)p * C);
-      acc(a0, d0);
+    for (int p = p_begin + pl; p < p_end; p += kGnPixBwd * lanes) {
+      GVec8 a[kGnPixBwd], d[kGnPixBwd];
+#pragma unroll
+      for (int u = 0; u < kGnPixBwd; ++u) {  // all loads first
+        const int pp = p + u * lanes;
+        if (pp < p_end) {
+          a[u].u = *reinterpret_cast<const uint4*>(xb + (int64_t)pp * C);
+          d[u].u = *reinterpret_cast<const uint4*>(db + (int64_t)pp * C);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kGnPixBwd; ++u)
+        if (p + u * lanes < p_end) acc(a[u], d[u]);
     }
   }
 #pragma unroll
@@ -319,25 +315,10 @@ __global__ void __launch_bounds__(512) groupnorm_bwd_reduce_kernel(
     s_b[tid * 8 + j] = active ? sb[j] : 0.f;
   }
   __syncthreads();
-  for (int c = tid; c < C; c += NT) {
-    const int vv = c >> 3, jj = c & 7;
-    float ta = 0.f, tb = 0.f;
-    for (int l = 0; l < lanes; ++l) {
-      ta += s_a[(l * V + vv) * 8 + jj];
-      tb += s_b[(l * V + vv) * 8 + jj];
-    }
-    c_a[c] = ta, c_b[c] = tb;
-  }
-  __syncthreads();
   const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
   for (int g = warp; g < G; g += nwarps) {
-    float ta = 0.f, tb = 0.f;
-    for (int c = g * cg + lane; c < (g + 1) * cg; c += 32) ta += c_a[c], tb += c_b[c];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      ta += __shfl_xor_sync(0xffffffffu, ta, off);
-      tb += __shfl_xor_sync(0xffffffffu, tb, off);
-    }
+    float ta, tb;
+    gn_group_sum2(s_a, s_b, g, cg, lanes, V, lane, ta, tb);
     if (lane == 0) {
       float* out = partial + (((int64_t)n * S + s) * G + g) * 2;
       out[0] = ta, out[1] = tb;
@@ -350,12 +331,22 @@ __global__ void __launch_bounds__(512) groupnorm_bwd_reduce_kernel(
   if (s_ticket != (unsigned)(S - 1)) return;
   __threadfence();
   const float inv_m = 1.f / ((float)HW * (float)cg);
-  for (int g = tid; g < G; g += NT) {
+  float* f_a = sm;  // re-use of the slots: [slices * G] x 2 (slices * G <= NT); fixed partition -> deterministic sums
+  float* f_b = sm + NT;
+  const int slices = (NT / G) > 0 ? (NT / G) : 1;
+  for (int idx = tid; idx < G * slices; idx += NT) {
+    const int g = idx % G, k = idx / G;
     float ta = 0.f, tb = 0.f;
-    for (int s2 = 0; s2 < S; ++s2) {  // fixed order: deterministic
+    for (int s2 = k; s2 < S; s2 += slices) {
       const float* p = partial + (((int64_t)n * S + s2) * G + g) * 2;
       ta += __ldcg(p), tb += __ldcg(p + 1);
     }
+    f_a[idx] = ta, f_b[idx] = tb;
+  }
+  __syncthreads();
+  for (int g = tid; g < G; g += NT) {
+    float ta = 0.f, tb = 0.f;
+    for (int k = 0; k < slices; ++k) ta += f_a[k * G + g], tb += f_b[k * G + g];
     ab[((int64_t)n * G + g) * 2] = ta * inv_m;
     ab[((int64_t)n * G + g) * 2 + 1] = tb * inv_m;
   }
@@ -403,21 +394,21 @@ __global__ void __launch_bounds__(512) groupnorm_bwd_apply_kernel(
     }
     return o;
   };
-  int p = p_begin + pl;
-  for (; p + lanes < p_end; p += 2 * lanes) {
-    GVec8 a0, a1, d0, d1;
-    a0.u = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
-    d0.u = *reinterpret_cast<const uint4*>(db + (int64_t)p * C);
-    a1.u = *reinterpret_cast<const uint4*>(xb + (int64_t)(p + lanes) * C);
-    d1.u = *reinterpret_cast<const uint4*>(db + (int64_t)(p + lanes) * C);
-    *reinterpret_cast<uint4*>(ob + (int64_t)p * C) = grad(a0, d0).u;
-    *reinterpret_cast<uint4*>(ob + (int64_t)(p + lanes) * C) = grad(a1, d1).u;
-  }
-  for (; p < p_end; p += lanes) {
-    GVec8 a0, d0;
-    a0.u = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
-    d0.u = *reinterpret_cast<const uint4*>(db + (int64_t)p * C);
-    *reinterpret_cast<uint4*>(ob + (int64_t)p * C) = grad(a0, d0).u;
+  for (int p = p_begin + pl; p < p_end; p += kGnPixBwd * lanes) {
+    GVec8 a[kGnPixBwd], d[kGnPixBwd];
+#pragma unroll
+    for (int u = 0; u < kGnPixBwd; ++u) {  // all loads first
+      const int pp = p + u * lanes;
+      if (pp < p_end) {
+        a[u].u = *reinterpret_cast<const uint4*>(xb + (int64_t)pp * C);
+        d[u].u = *reinterpret_cast<const uint4*>(db + (int64_t)pp * C);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGnPixBwd; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p_end) *reinterpret_cast<uint4*>(ob + (int64_t)pp * C) = grad(a[u], d[u]).u;
+    }
   }
 }
 
@@ -438,11 +429,10 @@ static GnLaunch gn_launch(int C) {
   return g;
 }
 
-// splits of a frame's pixels: `ctas` CTAs over the machine, at least `min_px` pixels per pixel lane and split
-static int gn_splits(int N, int HW, int lanes, int ctas, int min_px) {
-  int S = (ctas + N - 1) / N;
-  const int cap = HW / (lanes * min_px);
-  if (S > cap) S = cap;
+// splits of a frame's pixels: a thread owns `pix` pixels (one trip, all loads in flight) unless that needs more than
+// kGnMaxSplits splits (then it loops)
+static int gn_splits(int HW, int lanes, int pix) {
+  int S = (HW + lanes * pix - 1) / (lanes * pix);
   if (S > kGnMaxSplits) S = kGnMaxSplits;
   if (S < 1) S = 1;
   return S;
@@ -453,8 +443,8 @@ static int gn_check(const char* what, int N, int HW, int C, int G) {
     set_error("%s: non-positive dims", what);
     return MC_E_INVALID;
   }
-  if (C % 8 != 0 || C % G != 0 || C > 4096 || G > 256 || N > kGnTicketBytes / 4) {
-    set_error("%s: need C %% 8 == 0, C %% G == 0, C <= 4096, G <= 256, N <= 1024 (got N=%d C=%d G=%d)", what, N, C, G);
+  if (C % 8 != 0 || C % G != 0 || C > 4096 || G > 128 || N > kGnTicketBytes / 4) {
+    set_error("%s: need C %% 8 == 0, C %% G == 0, C <= 4096, G <= 128, N <= 1024 (got N=%d C=%d G=%d)", what, N, C, G);
     return MC_E_UNSUPPORTED;
   }
   return MC_OK;
@@ -502,8 +492,8 @@ extern "C" int mc_groupnorm_nhwc(const void* x, const void* chan_bias, int frame
   const GnLaunch L = gn_launch(C);
   const GnWorkspace w = gn_workspace(workspace, N, G);
   cudaStream_t st = (cudaStream_t)stream;
-  const int S1 = gn_splits(N, HW, L.lanes, 148 * 4, 8);
-  const int smem1 = (3 * L.NT * 8 + 3 * C) * (int)sizeof(float);
+  const int S1 = gn_splits(HW, L.lanes, kGnPixFwd);
+  const int smem1 = 2 * L.NT * 8 * (int)sizeof(float);
   if (smem1 > 48 * 1024)
     cudaFuncSetAttribute(groupnorm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
   groupnorm_stats_kernel<<<dim3(N, S1), L.NT, smem1, st>>>((const __half*)x, (const __half*)chan_bias,
@@ -512,7 +502,7 @@ extern "C" int mc_groupnorm_nhwc(const void* x, const void* chan_bias, int frame
   count_launch();
   rc = check_launch("groupnorm_stats");
   if (rc != MC_OK) return rc;
-  const int S2 = gn_splits(N, HW, L.lanes, 148 * 6, 4);
+  const int S2 = gn_splits(HW, L.lanes, kGnPixFwd);
   if (fuse_silu)
     groupnorm_apply_kernel<true><<<dim3(N, S2), L.NT, 0, st>>>((const __half*)x, (__half*)y, (const __half*)chan_bias,
                                                                frames_per_bias_row, w.finalised, (const __half*)gamma,
@@ -563,8 +553,8 @@ extern "C" int mc_groupnorm_nhwc_bwd(const void* x, const void* chan_bias, int f
   const GnLaunch L = gn_launch(C);
   const GnWorkspace w = gn_workspace(workspace, N, G);
   cudaStream_t st = (cudaStream_t)stream;
-  const int S1 = gn_splits(N, HW, L.lanes, 148 * 4, 4);
-  const int smem1 = (2 * L.NT * 8 + 2 * C) * (int)sizeof(float);
+  const int S1 = gn_splits(HW, L.lanes, kGnPixBwd);
+  const int smem1 = 2 * L.NT * 8 * (int)sizeof(float);
   const __half *xp = (const __half*)x, *cbp = (const __half*)chan_bias, *dzp = (const __half*)dz;
   const __half *gp = (const __half*)gamma, *bp = (const __half*)beta;
   if (fuse_silu) {
@@ -583,7 +573,7 @@ extern "C" int mc_groupnorm_nhwc_bwd(const void* x, const void* chan_bias, int f
   count_launch();
   rc = check_launch("groupnorm_bwd_reduce");
   if (rc != MC_OK) return rc;
-  const int S2 = gn_splits(N, HW, L.lanes, 148 * 6, 2);
+  const int S2 = gn_splits(HW, L.lanes, kGnPixBwd);
   if (fuse_silu)
     groupnorm_bwd_apply_kernel<true><<<dim3(N, S2), L.NT, 0, st>>>(xp, cbp, frames_per_bias_row, dzp, (__half*)dx,
                                                                    (const float*)stats, w.finalised, gp, bp, HW, C, G, S2,

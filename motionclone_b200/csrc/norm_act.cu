@@ -5,6 +5,7 @@
 //     motion_module.py:209)
 // GroupNorm lives in groupnorm.cu. Weights are frozen on this path (t2v_video_sample.py:67-68): input gradients only.
 #include <math.h>
+#include <stdlib.h>
 
 #include "mc_common.cuh"
 
@@ -24,56 +25,78 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
                                                         const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                                         const __half* __restrict__ post_add, int rows_per_frame, int frames,
                                                         int64_t rows, int C, float eps) {
+  constexpr int R = 2;  // rows per warp and trip: both rows' loads are issued before either reduction starts
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int V = C / 8;
-  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
-    const __half* xr = x + row * C;
-    Vec8 a[VPL];
-    float s = 0.f;
+  for (int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * R; row0 < rows; row0 += (int64_t)gridDim.x * 8 * R) {
+    Vec8 a[R][VPL];
+    float s[R];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + i * 32;
-      if (v < V) {
-        a[i].u = *reinterpret_cast<const uint4*>(xr + v * 8);
+    for (int r = 0; r < R; ++r) {
+      s[r] = 0.f;
+      const bool live = row0 + r < rows;
+      const __half* xr = x + (row0 + r) * C;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += __half2float(a[i].h[j]);
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + i * 32;
+        a[r][i].u = make_uint4(0u, 0u, 0u, 0u);
+        if (live && v < V) a[r][i].u = *reinterpret_cast<const uint4*>(xr + v * 8);
       }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    const float mean = s / (float)C;
-    float q = 0.f;
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + i * 32;
-      if (v < V) {
+      for (int i = 0; i < VPL; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = __half2float(a[i].h[j]) - mean;
-          q += d * d;
+        for (int j = 0; j < 8; ++j) s[r] += __half2float(a[r][i].h[j]);  // padding vectors are zeros
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], off);
+    float mean[R], q[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mean[r] = s[r] / (float)C;
+      q[r] = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + i * 32;
+        if (v < V) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = __half2float(a[r][i].h[j]) - mean[r];
+            q[r] += d * d;
+          }
         }
       }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
-    const float rstd = rsqrtf(q / (float)C + eps);
-    __half* yr = y + row * C;
-    const __half* pa = post_add ? post_add + (int64_t)((row / rows_per_frame) % frames) * C : nullptr;
+    for (int off = 16; off > 0; off >>= 1)
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + i * 32;
-      if (v < V) {
-        Vec8 w, b, o, pe;
-        w.u = *reinterpret_cast<const uint4*>(gamma + v * 8);
-        b.u = *reinterpret_cast<const uint4*>(beta + v * 8);
-        if (pa) pe.u = *reinterpret_cast<const uint4*>(pa + v * 8);
+      for (int r = 0; r < R; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], off);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float f = (__half2float(a[i].h[j]) - mean) * rstd * __half2float(w.h[j]) + __half2float(b.h[j]);
-          if (pa) f = round_half(f) + __half2float(pe.h[j]);  // eager: LayerNorm output (fp16) + pe (fp16)
-          o.h[j] = __float2half_rn(f);
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r;
+      if (row >= rows) break;
+      const float rstd = rsqrtf(q[r] / (float)C + eps);
+      __half* yr = y + row * C;
+      const __half* pa = post_add ? post_add + (int64_t)((row / rows_per_frame) % frames) * C : nullptr;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + i * 32;
+        if (v < V) {
+          Vec8 w, b, o, pe;
+          w.u = *reinterpret_cast<const uint4*>(gamma + v * 8);
+          b.u = *reinterpret_cast<const uint4*>(beta + v * 8);
+          if (pa) pe.u = *reinterpret_cast<const uint4*>(pa + v * 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float f = (__half2float(a[r][i].h[j]) - mean[r]) * rstd * __half2float(w.h[j]) + __half2float(b.h[j]);
+            if (pa) f = round_half(f) + __half2float(pe.h[j]);  // eager: LayerNorm output (fp16) + pe (fp16)
+            o.h[j] = __float2half_rn(f);
+          }
+          *reinterpret_cast<uint4*>(yr + v * 8) = o.u;
         }
-        *reinterpret_cast<uint4*>(yr + v * 8) = o.u;
       }
     }
   }
@@ -106,6 +129,67 @@ __global__ void __launch_bounds__(256) geglu_kernel(const __half* __restrict__ i
   }
 }
 
+// GEGLU through a lookup table. The erf-based kernel above is ISSUE-bound (~50 instructions per element: 127 us for the
+// 503 MB of the C = 320 layers, where HBM needs 77 us). fp16 has only 65 536 values, so fp16(gelu_erf(gate)) is a table
+// of 128 KB: built once per device with the SAME device code as geglu_kernel (bit-identical results), copied into shared
+// memory by one persistent 1024-thread CTA per SM, and `h * gelu` becomes one HMUL2 per pair (the product of two fp16
+// numbers is exact in fp32, so HMUL2's single rounding equals the eager fp32-multiply-then-round).
+__device__ __half g_gelu_lut[65536];
+
+__global__ void gelu_lut_init_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const __half x = __ushort_as_half((unsigned short)i);
+  g_gelu_lut[i] = __float2half_rn(gelu_erf(__half2float(x)));
+}
+
+__global__ void __launch_bounds__(1024) geglu_lut_kernel(const __half* __restrict__ in, __half* __restrict__ out, int64_t T,
+                                                         int I) {
+  extern __shared__ __align__(16) unsigned short s_lut[];  // 65536 entries
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(g_gelu_lut);
+    uint4* dst = reinterpret_cast<uint4*>(s_lut);
+    for (int i = threadIdx.x; i < 65536 / 8; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int VI = I / 8;
+  const int64_t nvec = T * VI;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto gate_mul = [&](const Vec8& hh, const Vec8& gg) {
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned lo = s_lut[__half_as_ushort(gg.h[2 * k])], hi = s_lut[__half_as_ushort(gg.h[2 * k + 1])];
+      const unsigned packed = lo | (hi << 16);
+      const __half2 prod = __hmul2(hh.h2[k], *reinterpret_cast<const __half2*>(&packed));
+      r[k] = *reinterpret_cast<const uint32_t*>(&prod);
+    }
+    return make_uint4(r[0], r[1], r[2], r[3]);
+  };
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; i + stride < nvec; i += 2 * stride) {  // two vectors per trip: 4 x 16 B in flight per thread
+    const int64_t i1 = i + stride;
+    const int64_t t0 = i / VI, t1 = i1 / VI;
+    const int v0 = (int)(i - t0 * VI), v1 = (int)(i1 - t1 * VI);
+    Vec8 h0, g0, h1, g1;
+    h0.u = *reinterpret_cast<const uint4*>(in + t0 * 2 * I + v0 * 8);
+    g0.u = *reinterpret_cast<const uint4*>(in + t0 * 2 * I + I + v0 * 8);
+    h1.u = *reinterpret_cast<const uint4*>(in + t1 * 2 * I + v1 * 8);
+    g1.u = *reinterpret_cast<const uint4*>(in + t1 * 2 * I + I + v1 * 8);
+    *reinterpret_cast<uint4*>(out + i * 8) = gate_mul(h0, g0);
+    *reinterpret_cast<uint4*>(out + i1 * 8) = gate_mul(h1, g1);
+  }
+  if (i < nvec) {
+    const int64_t t0 = i / VI;
+    const int v0 = (int)(i - t0 * VI);
+    Vec8 h0, g0;
+    h0.u = *reinterpret_cast<const uint4*>(in + t0 * 2 * I + v0 * 8);
+    g0.u = *reinterpret_cast<const uint4*>(in + t0 * 2 * I + I + v0 * 8);
+    *reinterpret_cast<uint4*>(out + i * 8) = gate_mul(h0, g0);
+  }
+}
+
+static bool g_gelu_lut_ready[64] = {};
+
 }  // namespace mc
 
 extern "C" int mc_layernorm(const void* x, void* y, const void* gamma, const void* beta, const void* post_add,
@@ -123,7 +207,7 @@ extern "C" int mc_layernorm(const void* x, void* y, const void* gamma, const voi
     set_error("layernorm: post_add needs rows_per_frame > 0 and frames > 0");
     return MC_E_INVALID;
   }
-  int64_t blocks = (rows + 7) / 8;
+  int64_t blocks = (rows + 15) / 16;  // 8 warps x 2 rows per CTA and trip
   if (blocks > 148 * 16) blocks = 148 * 16;
   cudaStream_t st = (cudaStream_t)stream;
   const int vpl = (C / 8 + 31) / 32;
@@ -157,9 +241,27 @@ extern "C" int mc_geglu(const void* in, void* out, int64_t T, int I, void* strea
     return MC_E_UNSUPPORTED;
   }
   const int64_t nvec = T * (I / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  static const int env_nolut = getenv("MC_GEGLU_NO_LUT") ? atoi(getenv("MC_GEGLU_NO_LUT")) : 0;  // A/B knob
+  int dev = 0, sms = 148;
+  if (!env_nolut && nvec >= (int64_t)1 << 20 && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+    // >= 16 MB of output: the persistent table kernel (one 1024-thread CTA per SM, 128 KB of shared memory)
+    if (!g_gelu_lut_ready[dev]) {  // once per device, ordered before the first use on this stream
+      gelu_lut_init_kernel<<<65536 / 256, 256, 0, st>>>();
+      count_launch();
+      int rc0 = check_launch("gelu_lut_init");
+      if (rc0 != MC_OK) return rc0;
+      cudaFuncSetAttribute(geglu_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 * 2);
+      g_gelu_lut_ready[dev] = true;
+    }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    geglu_lut_kernel<<<sms, 1024, 65536 * 2, st>>>((const __half*)in, (__half*)out, T, I);
+    count_launch();
+    return check_launch("geglu_lut");
+  }
   int64_t blocks = (nvec + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  geglu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)in, (__half*)out, T, I);
+  geglu_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __half*)in, (__half*)out, T, I);
   count_launch();
   return check_launch("geglu");
 }

@@ -29,8 +29,13 @@ from . import ops
 
 
 _XATTN_TC_HEAD_DIMS = (16, 32, 40, 64, 80, 160)  # instantiations of csrc/cross_attn_tc.cu
-# feed-forward row blocking (bytes of [rows, 8C] projection per block; 0 disables): see FeedForward._forward_l2_blocked
-_FF_CHUNK_BYTES = int(float(os.environ.get("MC_FF_CHUNK_MB", "32")) * (1 << 20))
+# Two measured-and-rejected experiments, kept behind knobs (profiles/README.md):
+# feed-forward row blocking (MB of [rows, 8C] projection per block; 0 = off): +4 ms per DDIM step on B200 — the smaller
+# GEMMs lose more than the L2-resident GEGLU gains. See FeedForward._forward_l2_blocked.
+_FF_CHUNK_BYTES = int(float(os.environ.get("MC_FF_CHUNK_MB", "0")) * (1 << 20))
+# tcgen05 short-sequence self-attention (csrc/self_attn_tc.cu): parity-green, but 70 us against the library's 37 us at
+# N = 256, DH = 160 (generic-load staging of 120 KB per CTA): the library kernel stays the default for `attn1`.
+_SELF_ATTN_TC = os.environ.get("MC_SELF_ATTN_TC", "0") == "1"
 
 
 def _frozen(*params) -> bool:
@@ -233,7 +238,8 @@ class CrossAttention(nn.Module):
             if self.processor is not None:
                 self.processor.record_qkv(self, hidden_states, qkv[:, :, 0].reshape(bf, n, inner),
                                           qkv[:, :, 1].reshape(bf, n, inner), qkv[:, :, 2].reshape(bf, n, inner), None)
-            if n <= ops.SELF_ATTN_SHORT_MAX_TOKENS and dh in ops.SELF_ATTN_SHORT_HEAD_DIMS and ops.glue_kernels_ok(qkv) \
+            if _SELF_ATTN_TC and n <= ops.SELF_ATTN_SHORT_MAX_TOKENS and dh in ops.SELF_ATTN_SHORT_HEAD_DIMS \
+                    and ops.glue_kernels_ok(qkv) \
                     and not (torch.is_grad_enabled() and qkv.requires_grad):
                 # 16x16 / 8x8 latent levels, inference passes: whole key axis in one TMEM tile (csrc/self_attn_tc.cu)
                 qkv3 = qkv.view(bf, n, 3 * inner)
