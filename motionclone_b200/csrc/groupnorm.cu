@@ -5,16 +5,18 @@
 // its own. These kernels read NHWC directly.
 //
 // HBM-bound: forward = 2 reads + 1 write of the tensor (statistics pass, then apply; the second read is an L2 hit for
-// tensors under ~60 MB), backward = 2 x (x, dz) reads + 1 write. What bounds a streaming kernel like this on B200 is
-// bytes in flight, so:
-//   * thread -> (8-channel vector column v, pixel lane): every access is a 128-bit load / store, a warp covers
-//     contiguous 512 B runs, and per-channel coefficients live in registers (no per-element integer division);
-//   * a frame is cut into enough splits that a thread owns <= 8 pixels (4 in the backward: two tensors) and issues ALL
-//     its loads before touching the data (8 x 16 B in flight per thread, one DRAM latency per CTA instead of one per
-//     loop trip);
-//   * inside a CTA (<= a few hundred samples per group) plain fp32 sums / sums of squares are reduced with adds only
-//     (shared memory, then one warp per group with shuffles); ACROSS splits the (count, mean, M2) partials are merged
-//     with Chan's formula (robust to |mean| >> std) by the LAST CTA of the frame (atomic ticket), which writes
+// tensors under ~60 MB), backward = 2 x (x, dz) reads + 1 write. What bounds a streaming kernel on B200 is bytes in
+// flight per SM, and register-staged loads cap that at 40-60 KB (measured: 26-40 % of the HBM roof, profiles/README.md).
+// So the tensor moves like the temporal-attention tiles do:
+//   * a CTA owns a CONTIGUOUS run of pixels of one frame and walks it in tiles of <= 32 KB, each brought in by ONE bulk
+//     copy (cp.async.bulk, TMA engine, SASS UBLKCP) signalled on an mbarrier, two stages deep: tile t+1 is in flight
+//     while tile t is consumed, so 3 resident CTAs keep ~190 KB per SM in flight with no registers held;
+//   * threads read the tile from shared memory with conflict-free 128-bit loads, thread -> (8-channel vector column,
+//     pixel lane), so per-channel coefficients live in registers (no per-element integer division);
+//   * the apply / backward-apply passes transform the tile IN PLACE and send it home with one bulk store;
+//   * statistics: inside a CTA (<= a few hundred samples per group) plain fp32 sums / sums of squares, reduced with adds
+//     only (shared memory, one warp per group, shuffles); ACROSS the splits of a frame the (count, mean, M2) partials are
+//     merged with Chan's formula (robust to |mean| >> std) by the LAST CTA of the frame (atomic ticket), which writes
 //     (mean, rstd): the apply pass reads 2 floats per group instead of re-folding the partials in every CTA.
 // Workspace layout (device memory, caller-owned): [4096 B tickets | N*G*2 floats finalised | N*S*G*3 floats partial].
 // The ticket region must be zero on first use; every call leaves it zero again.
@@ -29,10 +31,10 @@ union GVec8 {
   __half h[8];
 };
 
-constexpr int kGnTicketBytes = 4096;  // one uint32 per frame: N <= 1024
+constexpr int kGnTicketBytes = 4096;     // one uint32 per frame: N <= 1024
 constexpr int kGnMaxSplits = 128;
-constexpr int kGnPixFwd = 8;  // pixels per thread and trip (loads in flight): forward
-constexpr int kGnPixBwd = 4;  // backward (x and dz)
+constexpr int kGnTileBytes = 32 * 1024;  // shared-memory tile per CTA (forward: one tensor; backward: x and dz halves)
+constexpr int kGnHeader = 128;           // mbarrier
 
 // Chan et al. merge of (n, mean, M2) partials
 __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float meanb, float m2b) {
@@ -51,9 +53,6 @@ __device__ __forceinline__ float silu_grad(float y) {
   return s * (1.f + y * (1.f - s));
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// forward, pass 1: statistics. grid (N, S); thread -> (vector column v = tid % V, pixel lane pl = tid / V).
-// ---------------------------------------------------------------------------------------------------------------
 // sum over the (lanes x cg) per-(thread, channel) slots of group g held in shared memory; result valid in every lane
 __device__ __forceinline__ void gn_group_sum2(const float* __restrict__ s_a, const float* __restrict__ s_b, int g, int cg,
                                               int lanes, int V, int lane, float& ta, float& tb) {
@@ -71,53 +70,77 @@ __device__ __forceinline__ void gn_group_sum2(const float* __restrict__ s_a, con
   }
 }
 
-__global__ void __launch_bounds__(512) groupnorm_stats_kernel(const __half* __restrict__ x,
+// One bulk copy of pixels [p0, p0 + npx) of frame n into `buf`, completion on `bar` (issued by one thread).
+__device__ __forceinline__ void gn_fetch(uint8_t* buf, const __half* __restrict__ t, int n, int HW, int C, int p0, int npx,
+                                         uint64_t* bar) {
+  bulk_g2s(buf, t + ((int64_t)n * HW + p0) * C, (uint32_t)npx * C * 2, bar);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward, pass 1: statistics. grid (N, S); CTA = pixels [HW*s/S, HW*(s+1)/S) of frame n in trips of PX pixels.
+// thread -> (vector column v = tid % V, pixel lane pl = tid / V).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 2) groupnorm_stats_kernel(const __half* __restrict__ x,
                                                               const __half* __restrict__ chan_bias, int frames_per_row,
                                                               float* __restrict__ partial, float* __restrict__ stats,
                                                               unsigned* __restrict__ tickets, int HW, int C, int G, int S,
-                                                              int lanes, float eps) {
-  extern __shared__ float sm[];
+                                                              int lanes, int PX, float eps) {
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ unsigned s_ticket;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);  // bar[0], bar[1]: one per stage
+  uint8_t* buf = smem + kGnHeader;
+  float* s_sum = reinterpret_cast<float*>(smem + kGnHeader);  // [NT * 8], overlays the tiles once they have been consumed
   const int NT = blockDim.x, tid = threadIdx.x;
+  float* s_sq = s_sum + NT * 8;
   const int V = C / 8;
-  float* s_sum = sm;          // [NT * 8] per (thread, channel-of-vector)
-  float* s_sq = sm + NT * 8;
   const int n = blockIdx.x, s = blockIdx.y;
   const int v = tid % V, pl = tid / V;
   const bool active = pl < lanes;
   const int p_begin = (int)(((int64_t)HW * s) / S), p_end = (int)(((int64_t)HW * (s + 1)) / S);
+  const int ntrips = (p_end - p_begin + PX - 1) / PX;
+  const int stage_bytes = (PX * C * 2 + 127) / 128 * 128;
 
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto fetch = [&](int t) {  // one thread
+    const int p0 = p_begin + t * PX, npx = min(PX, p_end - p0);
+    mbar_arrive_expect_tx(bar + (t & 1), (uint32_t)npx * C * 2);
+    gn_fetch(buf + (t & 1) * stage_bytes, x, n, HW, C, p0, npx, bar + (t & 1));
+  };
+  if (tid == 0 && ntrips > 0) fetch(0);
   float sum[8], sq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
-  if (active) {
-    const __half* base = x + (int64_t)n * HW * C + v * 8;
-    const bool has_cb = chan_bias != nullptr;
-    for (int p = p_begin + pl; p < p_end; p += kGnPixFwd * lanes) {
-      GVec8 a[kGnPixFwd];
+  const bool has_cb = chan_bias != nullptr;
+  GVec8 cb;
+  cb.u = make_uint4(0u, 0u, 0u, 0u);
+  if (has_cb && active) cb.u = *reinterpret_cast<const uint4*>(chan_bias + (int64_t)(n / frames_per_row) * C + v * 8);
+  for (int t = 0; t < ntrips; ++t) {
+    if (tid == 0 && t + 1 < ntrips) fetch(t + 1);  // its stage was released by the barrier that ended trip t - 1
+    const int npx = min(PX, p_end - (p_begin + t * PX));
+    const uint8_t* tile = buf + (t & 1) * stage_bytes;
+    mbar_wait(bar + (t & 1), (t >> 1) & 1);
+    if (active) {
+#pragma unroll 2
+      for (int pp = pl; pp < npx; pp += lanes) {
+        GVec8 a;
+        a.u = *reinterpret_cast<const uint4*>(tile + ((int64_t)pp * C + v * 8) * 2);
 #pragma unroll
-      for (int u = 0; u < kGnPixFwd; ++u) {  // all loads first
-        const int pp = p + u * lanes;
-        a[u].u = make_uint4(0u, 0u, 0u, 0u);
-        if (pp < p_end) a[u].u = *reinterpret_cast<const uint4*>(base + (int64_t)pp * C);
-      }
-      GVec8 cb;
-      cb.u = make_uint4(0u, 0u, 0u, 0u);
-      if (has_cb) cb.u = *reinterpret_cast<const uint4*>(chan_bias + (int64_t)(n / frames_per_row) * C + v * 8);
-#pragma unroll
-      for (int u = 0; u < kGnPixFwd; ++u) {
-        if (p + u * lanes < p_end) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float f = __half2float(a[u].h[j]);
-            if (has_cb) f = round_half(f + __half2float(cb.h[j]));  // the eager `h + temb` is an fp16 tensor
-            sum[j] += f;
-            sq[j] = fmaf(f, f, sq[j]);
-          }
+        for (int j = 0; j < 8; ++j) {
+          float f = __half2float(a.h[j]);
+          if (has_cb) f = round_half(f + __half2float(cb.h[j]));  // the eager `h + temb` is an fp16 tensor
+          sum[j] += f;
+          sq[j] = fmaf(f, f, sq[j]);
         }
       }
     }
+    if (t + 1 < ntrips) __syncthreads();  // every thread is done with this stage
   }
+  __syncthreads();  // the tile is dead: its shared memory becomes the reduction slots
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     s_sum[tid * 8 + j] = active ? sum[j] : 0.f;
@@ -142,9 +165,9 @@ __global__ void __launch_bounds__(512) groupnorm_stats_kernel(const __half* __re
   __syncthreads();
   if (s_ticket != (unsigned)(S - 1)) return;
   __threadfence();
-  float* f_n = sm;  // re-use of the (sum, sq) slots: three arrays of NT floats (slices * G <= NT)
-  float* f_mean = sm + NT;
-  float* f_m2 = sm + 2 * NT;
+  float* f_n = s_sum;  // re-use of the slots: three arrays of NT floats (slices * G <= NT)
+  float* f_mean = s_sum + NT;
+  float* f_m2 = s_sum + 2 * NT;
   const int slices = (NT / G) > 0 ? (NT / G) : 1;
   for (int idx = tid; idx < G * slices; idx += NT) {
     const int g = idx % G, k = idx / G;
@@ -166,66 +189,88 @@ __global__ void __launch_bounds__(512) groupnorm_stats_kernel(const __half* __re
 }
 
 // forward, pass 2: y = a[c] * x + b[c] with a = rstd * gamma, b = beta - mean * a (ATen's fused-parameter form) [-> SiLU]
+// The tile is transformed in place in shared memory and leaves with one bulk store.
 template <bool SILU>
-__global__ void __launch_bounds__(512) groupnorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+__global__ void __launch_bounds__(512, 2) groupnorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                               const __half* __restrict__ chan_bias, int frames_per_row,
                                                               const float* __restrict__ stats,
                                                               const __half* __restrict__ gamma,
                                                               const __half* __restrict__ beta, int HW, int C, int G, int S,
-                                                              int lanes) {
+                                                              int lanes, int PX) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);  // bar[0], bar[1]
+  uint8_t* buf = smem + kGnHeader;
   const int tid = threadIdx.x, V = C / 8;
   const int n = blockIdx.x, s = blockIdx.y;
   const int v = tid % V, pl = tid / V;
-  if (pl >= lanes) return;
+  const bool active = pl < lanes;
   const int c0 = v * 8, cg = C / G;
   const int p_begin = (int)(((int64_t)HW * s) / S), p_end = (int)(((int64_t)HW * (s + 1)) / S);
-  const __half* xb = x + (int64_t)n * HW * C + c0;
-  __half* yb = y + (int64_t)n * HW * C + c0;
-  GVec8 in[kGnPixFwd];
-  auto load_batch = [&](int p) {
-#pragma unroll
-    for (int u = 0; u < kGnPixFwd; ++u) {
-      const int pp = p + u * lanes;
-      if (pp < p_end) in[u].u = *reinterpret_cast<const uint4*>(xb + (int64_t)pp * C);
-    }
+  const int ntrips = (p_end - p_begin + PX - 1) / PX;
+  const int stage_bytes = (PX * C * 2 + 127) / 128 * 128;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto fetch = [&](int t) {  // one thread
+    const int p0 = p_begin + t * PX, npx = min(PX, p_end - p0);
+    mbar_arrive_expect_tx(bar + (t & 1), (uint32_t)npx * C * 2);
+    gn_fetch(buf + (t & 1) * stage_bytes, x, n, HW, C, p0, npx, bar + (t & 1));
   };
-  int p = p_begin + pl;
-  if (p < p_end) load_batch(p);  // the tensor's loads go out before the (L2-resident) coefficient loads
+  if (tid == 0 && ntrips > 0) fetch(0);
+  // coefficients (L2-resident) while the first tile is in flight
   float a[8], b[8];
-  GVec8 w, bt, cb;
-  w.u = *reinterpret_cast<const uint4*>(gamma + c0);
-  bt.u = *reinterpret_cast<const uint4*>(beta + c0);
+  GVec8 cb;
   cb.u = make_uint4(0u, 0u, 0u, 0u);
   const bool has_cb = chan_bias != nullptr;
-  if (has_cb) cb.u = *reinterpret_cast<const uint4*>(chan_bias + (int64_t)(n / frames_per_row) * C + c0);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (c0 + j) / cg;
-    const float mean = stats[((int64_t)n * G + g) * 2], rstd = stats[((int64_t)n * G + g) * 2 + 1];
-    a[j] = rstd * __half2float(w.h[j]);
-    b[j] = fmaf(-mean, a[j], __half2float(bt.h[j]));
-  }
-  auto norm = [&](const GVec8& xin) {
-    GVec8 o;
+  if (active) {
+    GVec8 w, bt;
+    w.u = *reinterpret_cast<const uint4*>(gamma + c0);
+    bt.u = *reinterpret_cast<const uint4*>(beta + c0);
+    if (has_cb) cb.u = *reinterpret_cast<const uint4*>(chan_bias + (int64_t)(n / frames_per_row) * C + c0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float xv = __half2float(xin.h[j]);
-      if (has_cb) xv = round_half(xv + __half2float(cb.h[j]));
-      float f = fmaf(xv, a[j], b[j]);
-      if (SILU) f = silu_fwd(round_half(f));  // ATen rounds the GroupNorm output to fp16 before the separate SiLU kernel
-      o.h[j] = __float2half_rn(f);
+      const int g = (c0 + j) / cg;
+      const float mean = stats[((int64_t)n * G + g) * 2], rstd = stats[((int64_t)n * G + g) * 2 + 1];
+      a[j] = rstd * __half2float(w.h[j]);
+      b[j] = fmaf(-mean, a[j], __half2float(bt.h[j]));
     }
-    return o;
-  };
-  while (p < p_end) {
-#pragma unroll
-    for (int u = 0; u < kGnPixFwd; ++u) {
-      const int pp = p + u * lanes;
-      if (pp < p_end) *reinterpret_cast<uint4*>(yb + (int64_t)pp * C) = norm(in[u]).u;
-    }
-    p += kGnPixFwd * lanes;
-    if (p < p_end) load_batch(p);
   }
+  for (int t = 0; t < ntrips; ++t) {
+    if (tid == 0 && t + 1 < ntrips) {
+      if (t >= 1) bulk_wait_read_all();  // the store of trip t - 1 has finished reading the stage tile t + 1 lands in
+      fetch(t + 1);
+    }
+    const int p0 = p_begin + t * PX, npx = min(PX, p_end - p0);
+    uint8_t* tile = buf + (t & 1) * stage_bytes;
+    mbar_wait(bar + (t & 1), (t >> 1) & 1);
+    if (active) {
+#pragma unroll 2
+      for (int pp = pl; pp < npx; pp += lanes) {
+        uint4* slot = reinterpret_cast<uint4*>(tile + ((int64_t)pp * C + c0) * 2);
+        GVec8 in, o;
+        in.u = *slot;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float xv = __half2float(in.h[j]);
+          if (has_cb) xv = round_half(xv + __half2float(cb.h[j]));
+          float f = fmaf(xv, a[j], b[j]);
+          if (SILU) f = silu_fwd(round_half(f));  // ATen rounds the GroupNorm output to fp16 before the separate SiLU kernel
+          o.h[j] = __float2half_rn(f);
+        }
+        *slot = o.u;
+      }
+    }
+    fence_proxy_async();  // generic-proxy writes of the tile -> visible to the bulk-store engine
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(y + ((int64_t)n * HW + p0) * C, tile, (uint32_t)npx * C * 2);
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait_read_all();  // shared memory must outlive the last store's reads
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -258,57 +303,72 @@ __global__ void __launch_bounds__(512) groupnorm_bwd_reduce_kernel(
     const __half* __restrict__ x, const __half* __restrict__ chan_bias, int frames_per_row, const __half* __restrict__ dz,
     const float* __restrict__ stats, const __half* __restrict__ gamma, const __half* __restrict__ beta,
     float* __restrict__ partial, float* __restrict__ ab, unsigned* __restrict__ tickets, int HW, int C, int G, int S,
-    int lanes) {
-  extern __shared__ float sm[];
+    int lanes, int PX) {
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ unsigned s_ticket;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);  // bar[0], bar[1]
+  uint8_t* buf = smem + kGnHeader;                    // stage = [x tile | dz tile]
+  float* s_a = reinterpret_cast<float*>(smem + kGnHeader);  // [NT * 8], overlays the tiles once consumed
   const int NT = blockDim.x, tid = threadIdx.x, V = C / 8;
-  float* s_a = sm;  // [NT * 8]
-  float* s_b = sm + NT * 8;
+  float* s_b = s_a + NT * 8;
   const int n = blockIdx.x, s = blockIdx.y;
-  const int v = tid % V, pl = tid / V, cg = C / G;
+  const int v = tid % V, pl = tid / V, cg = C / G, c0 = v * 8;
   const bool active = pl < lanes;
   const int p_begin = (int)(((int64_t)HW * s) / S), p_end = (int)(((int64_t)HW * (s + 1)) / S);
+  const int ntrips = (p_end - p_begin + PX - 1) / PX;
+  const int tile_bytes = (PX * C * 2 + 127) / 128 * 128, stage_bytes = 2 * tile_bytes;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto fetch = [&](int t) {  // one thread
+    const int p0 = p_begin + t * PX, npx = min(PX, p_end - p0);
+    mbar_arrive_expect_tx(bar + (t & 1), 2u * (uint32_t)npx * C * 2);
+    gn_fetch(buf + (t & 1) * stage_bytes, x, n, HW, C, p0, npx, bar + (t & 1));
+    gn_fetch(buf + (t & 1) * stage_bytes + tile_bytes, dz, n, HW, C, p0, npx, bar + (t & 1));
+  };
+  if (tid == 0 && ntrips > 0) fetch(0);
   float sa[8], sb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sa[j] = sb[j] = 0.f;
+  GnBwdCoef k;
+  GVec8 cb;
+  cb.u = make_uint4(0u, 0u, 0u, 0u);
+  const bool has_cb = chan_bias != nullptr;
   if (active) {
-    const int c0 = v * 8;
-    GnBwdCoef k;
     gn_bwd_coef(k, stats, gamma, beta, n, c0, cg, G);
-    GVec8 cb;
-    cb.u = make_uint4(0u, 0u, 0u, 0u);
-    const bool has_cb = chan_bias != nullptr;
     if (has_cb) cb.u = *reinterpret_cast<const uint4*>(chan_bias + (int64_t)(n / frames_per_row) * C + c0);
-    const __half* xb = x + (int64_t)n * HW * C + c0;
-    const __half* db = dz + (int64_t)n * HW * C + c0;
-    auto acc = [&](const GVec8& a, const GVec8& d) {
+  }
+  for (int t = 0; t < ntrips; ++t) {
+    if (tid == 0 && t + 1 < ntrips) fetch(t + 1);
+    const int npx = min(PX, p_end - (p_begin + t * PX));
+    const uint8_t* tx = buf + (t & 1) * stage_bytes;
+    const uint8_t* td = tx + tile_bytes;
+    mbar_wait(bar + (t & 1), (t >> 1) & 1);
+    if (active) {
+#pragma unroll 2
+      for (int pp = pl; pp < npx; pp += lanes) {
+        GVec8 a, d;
+        a.u = *reinterpret_cast<const uint4*>(tx + ((int64_t)pp * C + c0) * 2);
+        d.u = *reinterpret_cast<const uint4*>(td + ((int64_t)pp * C + c0) * 2);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float xv = __half2float(a.h[j]);
-        if (has_cb) xv = round_half(xv + __half2float(cb.h[j]));
-        const float xh = (xv - k.mean[j]) * k.rstd[j];
-        float dy = __half2float(d.h[j]);
-        if (SILU) dy *= silu_grad(round_half(fmaf(xh, k.w[j], k.b[j])));
-        const float dxh = dy * k.w[j];
-        sa[j] += dxh;
-        sb[j] = fmaf(dxh, xh, sb[j]);
-      }
-    };
-    for (int p = p_begin + pl; p < p_end; p += kGnPixBwd * lanes) {
-      GVec8 a[kGnPixBwd], d[kGnPixBwd];
-#pragma unroll
-      for (int u = 0; u < kGnPixBwd; ++u) {  // all loads first
-        const int pp = p + u * lanes;
-        if (pp < p_end) {
-          a[u].u = *reinterpret_cast<const uint4*>(xb + (int64_t)pp * C);
-          d[u].u = *reinterpret_cast<const uint4*>(db + (int64_t)pp * C);
+        for (int j = 0; j < 8; ++j) {
+          float xv = __half2float(a.h[j]);
+          if (has_cb) xv = round_half(xv + __half2float(cb.h[j]));
+          const float xh = (xv - k.mean[j]) * k.rstd[j];
+          float dy = __half2float(d.h[j]);
+          if (SILU) dy *= silu_grad(round_half(fmaf(xh, k.w[j], k.b[j])));
+          const float dxh = dy * k.w[j];
+          sa[j] += dxh;
+          sb[j] = fmaf(dxh, xh, sb[j]);
         }
       }
-#pragma unroll
-      for (int u = 0; u < kGnPixBwd; ++u)
-        if (p + u * lanes < p_end) acc(a[u], d[u]);
     }
+    if (t + 1 < ntrips) __syncthreads();
   }
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     s_a[tid * 8 + j] = active ? sa[j] : 0.f;
@@ -331,13 +391,13 @@ __global__ void __launch_bounds__(512) groupnorm_bwd_reduce_kernel(
   if (s_ticket != (unsigned)(S - 1)) return;
   __threadfence();
   const float inv_m = 1.f / ((float)HW * (float)cg);
-  float* f_a = sm;  // re-use of the slots: [slices * G] x 2 (slices * G <= NT); fixed partition -> deterministic sums
-  float* f_b = sm + NT;
+  float* f_a = s_a;  // re-use of the slots: [slices * G] x 2 (slices * G <= NT); fixed partition -> deterministic sums
+  float* f_b = s_a + NT;
   const int slices = (NT / G) > 0 ? (NT / G) : 1;
   for (int idx = tid; idx < G * slices; idx += NT) {
-    const int g = idx % G, k = idx / G;
+    const int g = idx % G, kk = idx / G;
     float ta = 0.f, tb = 0.f;
-    for (int s2 = k; s2 < S; s2 += slices) {
+    for (int s2 = kk; s2 < S; s2 += slices) {
       const float* p = partial + (((int64_t)n * S + s2) * G + g) * 2;
       ta += __ldcg(p), tb += __ldcg(p + 1);
     }
@@ -346,70 +406,95 @@ __global__ void __launch_bounds__(512) groupnorm_bwd_reduce_kernel(
   __syncthreads();
   for (int g = tid; g < G; g += NT) {
     float ta = 0.f, tb = 0.f;
-    for (int k = 0; k < slices; ++k) ta += f_a[k * G + g], tb += f_b[k * G + g];
+    for (int kk = 0; kk < slices; ++kk) ta += f_a[kk * G + g], tb += f_b[kk * G + g];
     ab[((int64_t)n * G + g) * 2] = ta * inv_m;
     ab[((int64_t)n * G + g) * 2 + 1] = tb * inv_m;
   }
   if (tid == 0) tickets[n] = 0u;
 }
 
+// pass 2: dx over the dz tile, in place, then one bulk store
 template <bool SILU>
 __global__ void __launch_bounds__(512) groupnorm_bwd_apply_kernel(
     const __half* __restrict__ x, const __half* __restrict__ chan_bias, int frames_per_row, const __half* __restrict__ dz,
     __half* __restrict__ dx, const float* __restrict__ stats, const float* __restrict__ ab, const __half* __restrict__ gamma,
-    const __half* __restrict__ beta, int HW, int C, int G, int S, int lanes) {
+    const __half* __restrict__ beta, int HW, int C, int G, int S, int lanes, int PX) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);  // bar[0], bar[1]
+  uint8_t* buf = smem + kGnHeader;                    // stage = [x tile | dz tile]
   const int tid = threadIdx.x, V = C / 8;
   const int n = blockIdx.x, s = blockIdx.y;
   const int v = tid % V, pl = tid / V;
-  if (pl >= lanes) return;
+  const bool active = pl < lanes;
   const int c0 = v * 8, cg = C / G;
-  GnBwdCoef k;
-  gn_bwd_coef(k, stats, gamma, beta, n, c0, cg, G);
-  float ga[8], gb[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (c0 + j) / cg;
-    ga[j] = ab[((int64_t)n * G + g) * 2];
-    gb[j] = ab[((int64_t)n * G + g) * 2 + 1];
+  const int p_begin = (int)(((int64_t)HW * s) / S), p_end = (int)(((int64_t)HW * (s + 1)) / S);
+  const int ntrips = (p_end - p_begin + PX - 1) / PX;
+  const int tile_bytes = (PX * C * 2 + 127) / 128 * 128, stage_bytes = 2 * tile_bytes;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    fence_mbar_init();
   }
+  __syncthreads();
+  auto fetch = [&](int t) {  // one thread
+    const int p0 = p_begin + t * PX, npx = min(PX, p_end - p0);
+    mbar_arrive_expect_tx(bar + (t & 1), 2u * (uint32_t)npx * C * 2);
+    gn_fetch(buf + (t & 1) * stage_bytes, x, n, HW, C, p0, npx, bar + (t & 1));
+    gn_fetch(buf + (t & 1) * stage_bytes + tile_bytes, dz, n, HW, C, p0, npx, bar + (t & 1));
+  };
+  if (tid == 0 && ntrips > 0) fetch(0);
+  GnBwdCoef k;
+  float ga[8], gb[8];
   GVec8 cb;
   cb.u = make_uint4(0u, 0u, 0u, 0u);
   const bool has_cb = chan_bias != nullptr;
-  if (has_cb) cb.u = *reinterpret_cast<const uint4*>(chan_bias + (int64_t)(n / frames_per_row) * C + c0);
-  const int p_begin = (int)(((int64_t)HW * s) / S), p_end = (int)(((int64_t)HW * (s + 1)) / S);
-  const __half* xb = x + (int64_t)n * HW * C + c0;
-  const __half* db = dz + (int64_t)n * HW * C + c0;
-  __half* ob = dx + (int64_t)n * HW * C + c0;
-  auto grad = [&](const GVec8& a, const GVec8& d) {
-    GVec8 o;
+  if (active) {
+    gn_bwd_coef(k, stats, gamma, beta, n, c0, cg, G);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float xv = __half2float(a.h[j]);
-      if (has_cb) xv = round_half(xv + __half2float(cb.h[j]));
-      const float xh = (xv - k.mean[j]) * k.rstd[j];
-      float dy = __half2float(d.h[j]);
-      if (SILU) dy *= silu_grad(round_half(fmaf(xh, k.w[j], k.b[j])));
-      const float dxh = dy * k.w[j];
-      o.h[j] = __float2half_rn(k.rstd[j] * (dxh - ga[j] - xh * gb[j]));
+      const int g = (c0 + j) / cg;
+      ga[j] = ab[((int64_t)n * G + g) * 2];
+      gb[j] = ab[((int64_t)n * G + g) * 2 + 1];
     }
-    return o;
-  };
-  for (int p = p_begin + pl; p < p_end; p += kGnPixBwd * lanes) {
-    GVec8 a[kGnPixBwd], d[kGnPixBwd];
+    if (has_cb) cb.u = *reinterpret_cast<const uint4*>(chan_bias + (int64_t)(n / frames_per_row) * C + c0);
+  }
+  for (int t = 0; t < ntrips; ++t) {
+    if (tid == 0 && t + 1 < ntrips) {
+      if (t >= 1) bulk_wait_read_all();  // the store of trip t - 1 has finished reading the stage tile t + 1 lands in
+      fetch(t + 1);
+    }
+    const int p0 = p_begin + t * PX, npx = min(PX, p_end - p0);
+    const uint8_t* tx = buf + (t & 1) * stage_bytes;
+    uint8_t* td = buf + (t & 1) * stage_bytes + tile_bytes;
+    mbar_wait(bar + (t & 1), (t >> 1) & 1);
+    if (active) {
+#pragma unroll 2
+      for (int pp = pl; pp < npx; pp += lanes) {
+        uint4* dslot = reinterpret_cast<uint4*>(td + ((int64_t)pp * C + c0) * 2);
+        GVec8 a, d, o;
+        a.u = *reinterpret_cast<const uint4*>(tx + ((int64_t)pp * C + c0) * 2);
+        d.u = *dslot;
 #pragma unroll
-    for (int u = 0; u < kGnPixBwd; ++u) {  // all loads first
-      const int pp = p + u * lanes;
-      if (pp < p_end) {
-        a[u].u = *reinterpret_cast<const uint4*>(xb + (int64_t)pp * C);
-        d[u].u = *reinterpret_cast<const uint4*>(db + (int64_t)pp * C);
+        for (int j = 0; j < 8; ++j) {
+          float xv = __half2float(a.h[j]);
+          if (has_cb) xv = round_half(xv + __half2float(cb.h[j]));
+          const float xh = (xv - k.mean[j]) * k.rstd[j];
+          float dy = __half2float(d.h[j]);
+          if (SILU) dy *= silu_grad(round_half(fmaf(xh, k.w[j], k.b[j])));
+          const float dxh = dy * k.w[j];
+          o.h[j] = __float2half_rn(k.rstd[j] * (dxh - ga[j] - xh * gb[j]));
+        }
+        *dslot = o.u;
       }
     }
-#pragma unroll
-    for (int u = 0; u < kGnPixBwd; ++u) {
-      const int pp = p + u * lanes;
-      if (pp < p_end) *reinterpret_cast<uint4*>(ob + (int64_t)pp * C) = grad(a[u], d[u]).u;
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(dx + ((int64_t)n * HW + p0) * C, td, (uint32_t)npx * C * 2);
+      bulk_commit();
     }
   }
+  if (tid == 0) bulk_wait_read_all();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -429,13 +514,35 @@ static GnLaunch gn_launch(int C) {
   return g;
 }
 
-// splits of a frame's pixels: a thread owns `pix` pixels (one trip, all loads in flight) unless that needs more than
-// kGnMaxSplits splits (then it loops)
-static int gn_splits(int HW, int lanes, int pix) {
-  int S = (HW + lanes * pix - 1) / (lanes * pix);
-  if (S > kGnMaxSplits) S = kGnMaxSplits;
-  if (S < 1) S = 1;
-  return S;
+// Tiling of a frame: PX pixels (one bulk copy of <= `tile_bytes` per tensor) per trip, S splits (CTAs) per frame; a CTA
+// makes more than one trip only when the frame would need more than kGnMaxSplits splits.
+struct GnTiling {
+  int PX, S, smem;
+};
+
+// `tensors` tiles of <= tile_bytes each per stage, two stages. Enough CTAs to fill the machine three deep; beyond that a
+// CTA walks up to 4 tiles (fewer prologues / reduction tails per byte).
+static GnTiling gn_tiling(int N, int HW, int C, int NT, int tensors, int tile_bytes) {
+  GnTiling t;
+  t.PX = tile_bytes / (C * 2);
+  if (t.PX < 1) t.PX = 1;
+  if (t.PX > HW) t.PX = HW;
+  const int tiles = (HW + t.PX - 1) / t.PX;
+  int trips = (int)(((int64_t)N * tiles) / (148 * 3));
+  if (trips < 1) trips = 1;
+  if (trips > 4) trips = 4;
+  t.S = (tiles + trips - 1) / trips;
+  if (t.S > kGnMaxSplits) t.S = kGnMaxSplits;
+  const int tile = (t.PX * C * 2 + 127) / 128 * 128;
+  const int stages = 2 * tensors * tile;
+  const int slots = 2 * NT * 8 * (int)sizeof(float);  // reduction slots overlay the tiles
+  t.smem = kGnHeader + (stages > slots ? stages : slots);
+  return t;
+}
+
+template <typename K>
+static void gn_allow_smem(K kern, int smem) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 static int gn_check(const char* what, int N, int HW, int C, int G) {
@@ -492,25 +599,25 @@ extern "C" int mc_groupnorm_nhwc(const void* x, const void* chan_bias, int frame
   const GnLaunch L = gn_launch(C);
   const GnWorkspace w = gn_workspace(workspace, N, G);
   cudaStream_t st = (cudaStream_t)stream;
-  const int S1 = gn_splits(HW, L.lanes, kGnPixFwd);
-  const int smem1 = 2 * L.NT * 8 * (int)sizeof(float);
-  if (smem1 > 48 * 1024)
-    cudaFuncSetAttribute(groupnorm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-  groupnorm_stats_kernel<<<dim3(N, S1), L.NT, smem1, st>>>((const __half*)x, (const __half*)chan_bias,
-                                                           frames_per_bias_row, w.partial, w.finalised, w.tickets, HW, C, G,
-                                                           S1, L.lanes, eps);
+  const GnTiling T = gn_tiling(N, HW, C, L.NT, 1, kGnTileBytes);
+  gn_allow_smem(groupnorm_stats_kernel, T.smem);
+  groupnorm_stats_kernel<<<dim3(N, T.S), L.NT, T.smem, st>>>((const __half*)x, (const __half*)chan_bias,
+                                                             frames_per_bias_row, w.partial, w.finalised, w.tickets, HW, C,
+                                                             G, T.S, L.lanes, T.PX, eps);
   count_launch();
   rc = check_launch("groupnorm_stats");
   if (rc != MC_OK) return rc;
-  const int S2 = gn_splits(HW, L.lanes, kGnPixFwd);
-  if (fuse_silu)
-    groupnorm_apply_kernel<true><<<dim3(N, S2), L.NT, 0, st>>>((const __half*)x, (__half*)y, (const __half*)chan_bias,
-                                                               frames_per_bias_row, w.finalised, (const __half*)gamma,
-                                                               (const __half*)beta, HW, C, G, S2, L.lanes);
-  else
-    groupnorm_apply_kernel<false><<<dim3(N, S2), L.NT, 0, st>>>((const __half*)x, (__half*)y, (const __half*)chan_bias,
-                                                                frames_per_bias_row, w.finalised, (const __half*)gamma,
-                                                                (const __half*)beta, HW, C, G, S2, L.lanes);
+  if (fuse_silu) {
+    gn_allow_smem(groupnorm_apply_kernel<true>, T.smem);
+    groupnorm_apply_kernel<true><<<dim3(N, T.S), L.NT, T.smem, st>>>(
+        (const __half*)x, (__half*)y, (const __half*)chan_bias, frames_per_bias_row, w.finalised, (const __half*)gamma,
+        (const __half*)beta, HW, C, G, T.S, L.lanes, T.PX);
+  } else {
+    gn_allow_smem(groupnorm_apply_kernel<false>, T.smem);
+    groupnorm_apply_kernel<false><<<dim3(N, T.S), L.NT, T.smem, st>>>(
+        (const __half*)x, (__half*)y, (const __half*)chan_bias, frames_per_bias_row, w.finalised, (const __half*)gamma,
+        (const __half*)beta, HW, C, G, T.S, L.lanes, T.PX);
+  }
   count_launch();
   return check_launch("groupnorm_apply");
 }
@@ -553,35 +660,36 @@ extern "C" int mc_groupnorm_nhwc_bwd(const void* x, const void* chan_bias, int f
   const GnLaunch L = gn_launch(C);
   const GnWorkspace w = gn_workspace(workspace, N, G);
   cudaStream_t st = (cudaStream_t)stream;
-  const int S1 = gn_splits(HW, L.lanes, kGnPixBwd);
-  const int smem1 = 2 * L.NT * 8 * (int)sizeof(float);
+  const GnTiling T = gn_tiling(N, HW, C, L.NT, 2, kGnTileBytes / 2);
   const __half *xp = (const __half*)x, *cbp = (const __half*)chan_bias, *dzp = (const __half*)dz;
   const __half *gp = (const __half*)gamma, *bp = (const __half*)beta;
   if (fuse_silu) {
-    if (smem1 > 48 * 1024)
-      cudaFuncSetAttribute(groupnorm_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-    groupnorm_bwd_reduce_kernel<true><<<dim3(N, S1), L.NT, smem1, st>>>(xp, cbp, frames_per_bias_row, dzp,
-                                                                        (const float*)stats, gp, bp, w.partial, w.finalised,
-                                                                        w.tickets, HW, C, G, S1, L.lanes);
+    gn_allow_smem(groupnorm_bwd_reduce_kernel<true>, T.smem);
+    groupnorm_bwd_reduce_kernel<true><<<dim3(N, T.S), L.NT, T.smem, st>>>(xp, cbp, frames_per_bias_row, dzp,
+                                                                          (const float*)stats, gp, bp, w.partial,
+                                                                          w.finalised, w.tickets, HW, C, G, T.S, L.lanes,
+                                                                          T.PX);
   } else {
-    if (smem1 > 48 * 1024)
-      cudaFuncSetAttribute(groupnorm_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-    groupnorm_bwd_reduce_kernel<false><<<dim3(N, S1), L.NT, smem1, st>>>(xp, cbp, frames_per_bias_row, dzp,
-                                                                         (const float*)stats, gp, bp, w.partial,
-                                                                         w.finalised, w.tickets, HW, C, G, S1, L.lanes);
+    gn_allow_smem(groupnorm_bwd_reduce_kernel<false>, T.smem);
+    groupnorm_bwd_reduce_kernel<false><<<dim3(N, T.S), L.NT, T.smem, st>>>(xp, cbp, frames_per_bias_row, dzp,
+                                                                           (const float*)stats, gp, bp, w.partial,
+                                                                           w.finalised, w.tickets, HW, C, G, T.S, L.lanes,
+                                                                           T.PX);
   }
   count_launch();
   rc = check_launch("groupnorm_bwd_reduce");
   if (rc != MC_OK) return rc;
-  const int S2 = gn_splits(HW, L.lanes, kGnPixBwd);
-  if (fuse_silu)
-    groupnorm_bwd_apply_kernel<true><<<dim3(N, S2), L.NT, 0, st>>>(xp, cbp, frames_per_bias_row, dzp, (__half*)dx,
-                                                                   (const float*)stats, w.finalised, gp, bp, HW, C, G, S2,
-                                                                   L.lanes);
-  else
-    groupnorm_bwd_apply_kernel<false><<<dim3(N, S2), L.NT, 0, st>>>(xp, cbp, frames_per_bias_row, dzp, (__half*)dx,
-                                                                    (const float*)stats, w.finalised, gp, bp, HW, C, G, S2,
-                                                                    L.lanes);
+  if (fuse_silu) {
+    gn_allow_smem(groupnorm_bwd_apply_kernel<true>, T.smem);
+    groupnorm_bwd_apply_kernel<true><<<dim3(N, T.S), L.NT, T.smem, st>>>(xp, cbp, frames_per_bias_row, dzp, (__half*)dx,
+                                                                         (const float*)stats, w.finalised, gp, bp, HW, C, G,
+                                                                         T.S, L.lanes, T.PX);
+  } else {
+    gn_allow_smem(groupnorm_bwd_apply_kernel<false>, T.smem);
+    groupnorm_bwd_apply_kernel<false><<<dim3(N, T.S), L.NT, T.smem, st>>>(xp, cbp, frames_per_bias_row, dzp, (__half*)dx,
+                                                                          (const float*)stats, w.finalised, gp, bp, HW, C,
+                                                                          G, T.S, L.lanes, T.PX);
+  }
   count_launch();
   return check_launch("groupnorm_bwd_apply");
 }
