@@ -520,18 +520,18 @@ struct GnTiling {
   int PX, S, smem;
 };
 
-// `tensors` tiles of <= tile_bytes each per stage, two stages. Enough CTAs to fill the machine three deep; beyond that a
-// CTA walks up to 4 tiles (fewer prologues / reduction tails per byte).
-static GnTiling gn_tiling(int N, int HW, int C, int NT, int tensors, int tile_bytes) {
+// `tensors` tiles of <= tile_bytes each per stage, two stages (64 KB per CTA -> 3 CTAs per SM; the backward kernels hold
+// more registers: 2). ONE wave: at most 148 x ctas_per_sm CTAs in the grid, each walking ceil(tiles / S) tiles through its two-stage pipeline (a grid of 1.5 waves costs
+// two: measured on the 16 x 64 x 64 x 320 layers).
+static GnTiling gn_tiling(int N, int HW, int C, int NT, int tensors, int tile_bytes, int ctas_per_sm) {
   GnTiling t;
   t.PX = tile_bytes / (C * 2);
   if (t.PX < 1) t.PX = 1;
   if (t.PX > HW) t.PX = HW;
   const int tiles = (HW + t.PX - 1) / t.PX;
-  int trips = (int)(((int64_t)N * tiles) / (148 * 3));
-  if (trips < 1) trips = 1;
-  if (trips > 4) trips = 4;
-  t.S = (tiles + trips - 1) / trips;
+  t.S = (148 * ctas_per_sm) / N;
+  if (t.S < 1) t.S = 1;
+  if (t.S > tiles) t.S = tiles;
   if (t.S > kGnMaxSplits) t.S = kGnMaxSplits;
   const int tile = (t.PX * C * 2 + 127) / 128 * 128;
   const int stages = 2 * tensors * tile;
@@ -599,7 +599,7 @@ extern "C" int mc_groupnorm_nhwc(const void* x, const void* chan_bias, int frame
   const GnLaunch L = gn_launch(C);
   const GnWorkspace w = gn_workspace(workspace, N, G);
   cudaStream_t st = (cudaStream_t)stream;
-  const GnTiling T = gn_tiling(N, HW, C, L.NT, 1, kGnTileBytes);
+  const GnTiling T = gn_tiling(N, HW, C, L.NT, 1, kGnTileBytes, 3);
   gn_allow_smem(groupnorm_stats_kernel, T.smem);
   groupnorm_stats_kernel<<<dim3(N, T.S), L.NT, T.smem, st>>>((const __half*)x, (const __half*)chan_bias,
                                                              frames_per_bias_row, w.partial, w.finalised, w.tickets, HW, C,
@@ -660,7 +660,7 @@ extern "C" int mc_groupnorm_nhwc_bwd(const void* x, const void* chan_bias, int f
   const GnLaunch L = gn_launch(C);
   const GnWorkspace w = gn_workspace(workspace, N, G);
   cudaStream_t st = (cudaStream_t)stream;
-  const GnTiling T = gn_tiling(N, HW, C, L.NT, 2, kGnTileBytes / 2);
+  const GnTiling T = gn_tiling(N, HW, C, L.NT, 2, kGnTileBytes / 2, 2);
   const __half *xp = (const __half*)x, *cbp = (const __half*)chan_bias, *dzp = (const __half*)dz;
   const __half *gp = (const __half*)gamma, *bp = (const __half*)beta;
   if (fuse_silu) {
