@@ -249,13 +249,16 @@ def run_own_arm(args):
     clocks = ClockSampler(local)
     clocks.start()
     _lib.reset_launch_count()
-    ops.TIMER = ops.KernelTimer()
     ms = timed(step_resident, args.steps, args.warmup)
     launches = _lib.launch_count()
-    ksum = ops.TIMER.summary()
-    ops.TIMER = None
     ms_e2e = timed(step_e2e, args.steps, args.warmup + args.steps)
     clk = clocks.finish()
+    # roofline leg: ONE more sample with a CUDA-event pair around every launch of this package's attention kernels (on the
+    # launching stream). Kept out of the timed regions above: ~8 000 event records per sample cost ~3 % of the step.
+    ops.TIMER = ops.KernelTimer()
+    step_resident(args.warmup)
+    ksum = ops.TIMER.summary()
+    ops.TIMER = None
 
     frames = L * args.steps * world
     value = frames / (ms / 1e3)
@@ -281,6 +284,12 @@ def run_own_arm(args):
     b_l, b_b, b_ms = ksum.get("temporal_attn_bwd", (0, 0, 0.0))
     if b_ms > 0:
         roof["bwd"] = {"launches": b_l, "achieved": (b_b / 1e9) / (b_ms / 1e3), "frac": (b_b / 1e9) / (b_ms / 1e3) / peak}
+    roof["measured_on"] = "one extra sample after the timed regions (event pairs around every launch)"
+    # the other hand-written attention kernels, same accounting (algorithmic bytes / event time), for the record
+    roof["other_kernels"] = {
+        k: {"launches": n_, "achieved": (b_ / 1e9) / (ms_ / 1e3), "frac": (b_ / 1e9) / (ms_ / 1e3) / peak,
+            "avg_launch_us": 1e3 * ms_ / n_}
+        for k, (n_, b_, ms_) in ksum.items() if k.startswith("cross_attn") and ms_ > 0}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         tg, tp, info = cpu_reference_steps(args.cpu_budget, infer)
