@@ -1,30 +1,27 @@
 #!/bin/bash
 # ncu evidence for profiles/ (run under gpurun, ONE GPU). Numbers printed by runs under ncu are never bench values.
+# Reports are exported to CSV on the box and the .ncu-rep files dropped (gpurun_out/ is capped at 64 MiB).
 set -u
 OUT=gpurun_out
 mkdir -p $OUT
 TAG=${1:-r01}
-# 1. every launch of a reduced-step bench run with its device time (cold-cache, serialised: compare SHARES)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${TAG}_launches_bench.csv \
-  python bench.py --steps 1 --warmup 0 --ddim-steps 2 --no-cpu-baseline > $OUT/${TAG}_launches_bench.stdout 2> $OUT/${TAG}_launches_bench.stderr
-echo "launch list rc=$?"
-# 2. full captures of the hand-written kernels (first launches of the microbenchmarks: 16 x 64 x 64 x 320 layer shapes)
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:temporal_attn_fwd_kernel -c 2 -f -o $OUT/${TAG}_temporal_fwd \
-  python scripts/kernel_bench.py --ncu > /dev/null 2>&1
-echo "temporal fwd rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:temporal_attn_bwd_kernel -c 1 -f -o $OUT/${TAG}_temporal_bwd \
-  python scripts/kernel_bench.py --ncu > /dev/null 2>&1
-echo "temporal bwd rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:cross_attn -c 1 -f -o $OUT/${TAG}_cross_attn_fwd \
-  python scripts/xattn_bench.py > /dev/null 2>&1
-echo "cross fwd rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:cross_attn_bwd -c 1 -f -o $OUT/${TAG}_cross_attn_bwd \
-  python scripts/xattn_bench.py > /dev/null 2>&1
-echo "cross bwd rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:groupnorm -c 2 -f -o $OUT/${TAG}_groupnorm_fwd \
-  python scripts/glue_bench.py > /dev/null 2>&1
-echo "groupnorm rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:geglu_lut -c 1 -f -o $OUT/${TAG}_geglu_lut \
-  python scripts/glue_bench.py > /dev/null 2>&1
-echo "geglu rc=$?"
-ls -la $OUT | tail -n 15
+full() {  # name, kernel regex, count, command...
+  local name=$1 rx=$2 cnt=$3; shift 3
+  timeout 240 ncu --set full --clock-control none -k regex:$rx -c $cnt -f -o /tmp/${name} "$@" > /dev/null 2>&1
+  echo "$name rc=$?"
+  ncu -i /tmp/${name}.ncu-rep --page raw --csv > $OUT/${TAG}_ncu_${name}_raw.csv 2>/dev/null
+  ncu -i /tmp/${name}.ncu-rep --page details --csv > $OUT/${TAG}_ncu_${name}_details.csv 2>/dev/null
+}
+full temporal_fwd temporal_attn_fwd_kernel 2 python scripts/kernel_bench.py --ncu
+full temporal_bwd temporal_attn_bwd_kernel 1 python scripts/kernel_bench.py --ncu
+full cross_attn_fwd cross_attn_fwd 1 python scripts/xattn_bench.py
+full cross_attn_bwd cross_attn_bwd 1 python scripts/xattn_bench.py
+full groupnorm_fwd groupnorm 2 python scripts/glue_bench.py
+if [ "${2:-}" = "launches" ]; then
+  # every launch of one guided + one plain DDIM step with its device time (cold-cache, serialised: compare SHARES)
+  timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file $OUT/${TAG}_launches_step.csv \
+    python scripts/launch_list_step.py > $OUT/${TAG}_launches_step.stdout 2>&1
+  echo "launch list rc=$?"
+  gzip -f $OUT/${TAG}_launches_step.csv
+fi
+du -sh $OUT; ls -la $OUT | tail -n 14
