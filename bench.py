@@ -106,20 +106,24 @@ def cpu_reference_steps(budget_s: float, infer: dict):
     acp = O.alphas_cumprod()
     lat, text = inp["noisy_latents"], inp["text_embeddings"]
     start = time.time()
-    # bounded sample: the b=1 forward on the first PROBE_FRAMES of the 16 frames (same resolution, weights and ops; cost is
-    # linear in frames to < 1 %: temporal attention is 0.1 % of the flops), scaled by L / PROBE_FRAMES. Measured on the
-    # round-1 box (128 threads): a full plain step takes 258 s and a guided step 533 s, far beyond any bench budget.
-    PROBE_FRAMES = 2
+    # bounded sample: one b=1 UNet forward with ALL 16 frames (the host threads parallelise over the frame batch exactly as
+    # in the full problem) at a quarter of the pixels (16 x 256 x 256), scaled by the analytic FLOP ratio of the two
+    # problem sizes (17.67 vs 4.08 TFLOP per forward; the quadratic spatial self-attention term is why it is
+    # 4.33 and not 4). Measured on the round-1 box (128 threads): a full plain step takes 258 s and a guided step 533 s,
+    # far beyond any bench budget. (A 2-of-16-frames probe was tried first and overestimates 7x: too little batch
+    # parallelism for 128 threads.)
+    PROBE_HW, PROBE_SCALE = 256, 17.67 / 4.08
+    probe = synthetic_inputs(L, PROBE_HW, PROBE_HW, 768, 42)["noisy_latents"]
     with torch.no_grad():
         t0 = time.time()
-        O.unet_forward(sd, UNET_SD15_CONFIG, lat[:, :, :PROBE_FRAMES].contiguous(), int(timesteps[0]), text[[0]])
+        O.unet_forward(sd, UNET_SD15_CONFIG, probe, int(timesteps[0]), text[[0]])
         t_probe = time.time() - t0
-    t_fwd = t_probe * L / PROBE_FRAMES
-    log(f"[cpu] b=1 UNet forward on {PROBE_FRAMES}/{L} frames {t_probe:.1f}s -> {t_fwd:.1f}s per full forward")
+    t_fwd = t_probe * PROBE_SCALE
+    log(f"[cpu] b=1 UNet forward at {L}x{PROBE_HW}x{PROBE_HW} {t_probe:.1f}s -> {t_fwd:.1f}s per full forward")
     info = dict(cores=cores, s_per_forward=t_fwd,
-                measured=f"one b=1 UNet forward on {PROBE_FRAMES} of {L} frames, scaled x{L // PROBE_FRAMES}; steps "
-                         f"extrapolated with {GUIDED_FWD_EQUIV:.2f} / {PLAIN_FWD_EQUIV:.2f} forward-equivalents per "
-                         "guided / plain step")
+                measured=f"one b=1 UNet forward at {L}x{PROBE_HW}x{PROBE_HW} ({t_probe:.1f} s), scaled by the analytic "
+                         f"FLOP ratio {PROBE_SCALE:.2f}; steps extrapolated with {GUIDED_FWD_EQUIV:.2f} / "
+                         f"{PLAIN_FWD_EQUIV:.2f} forward-equivalents per guided / plain step")
     if (time.time() - start) + 1.3 * t_fwd < budget_s:
         with torch.no_grad():
             t0 = time.time()
