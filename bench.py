@@ -28,6 +28,8 @@ import torch  # noqa: E402
 
 METRIC = "frames/sec at 16x512x512 T2V, 50-step DDIM"
 UNIT = "frames/s"
+WORKLOAD = ("t2v_object 16x512x512, 50-step DDIM (30 guided, guidance_scale 0.4), random-init SD1.5 + v3_sd15_mm widths, "
+            "1 sample per step per GPU")
 INFER = dict(cfg_scale=7.5, negative_prompt="", warm_up_steps=10, cool_up_steps=10, motion_guidance_weight=2000,
              motion_guidance_blocks=["up_blocks.1"], add_noise_step=400, inference_steps=50, guidance_steps=30,
              guidance_scale=0.4, video_length=16, height=512, width=512, new_prompt="synthetic")
@@ -166,7 +168,9 @@ def run_reference_arm(args):
             "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * infer["video_length"] / fps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "t2v_object 16x512x512, 50-step DDIM (30 guided), SD1.5+mm widths, CPU oracle port"},
+            "config": {"workload": WORKLOAD, "ddim_steps": infer["inference_steps"],
+                       "guided_steps": infer["guidance_steps"],
+                       "parallelism": f"reference CPU path (oracle port, fp32, {info['cores']} host threads), rank 0 only"},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": sample,
                              "s_per_guided_step": tg, "s_per_plain_step": tp, "s_per_forward": info["s_per_forward"]},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -305,8 +309,7 @@ def run_own_arm(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "t2v_object 16x512x512, 50-step DDIM (30 guided, guidance_scale 0.4), random-init "
-                                   "SD1.5 + v3_sd15_mm widths, 1 sample per step per GPU",
+            "config": {"workload": WORKLOAD,
                        "ddim_steps": infer["inference_steps"], "guided_steps": infer["guidance_steps"],
                        "parallelism": f"replica x{world} (independent samples), one broadcast of the motion representation",
                        "l2": "inputs larger than L2 (2.6 GB weights stream every UNet forward)",
