@@ -21,6 +21,12 @@
 
 #include "mc_common.cuh"
 
+// The file can be compiled as two translation units (build time): -DMC_TA_PART=1 keeps the forward entry point and its
+// instantiations, =2 the backward ones; undefined / 0 keeps both.
+#ifndef MC_TA_PART
+#define MC_TA_PART 0
+#endif
+
 namespace mc {
 
 constexpr int kHeaderBytes = 128;
@@ -972,6 +978,7 @@ static int launch_bwd(TAParams& prm, cudaStream_t st) {
     default: break;                                         \
   }
 
+#if MC_TA_PART != 2
 static int dispatch_fwd(TAParams& prm, int L, int DH, cudaStream_t st) {
   if (L == 8) { MC_DISPATCH_DH(8, launch_fwd) }
   if (L == 16) { MC_DISPATCH_DH(16, launch_fwd) }
@@ -980,6 +987,8 @@ static int dispatch_fwd(TAParams& prm, int L, int DH, cudaStream_t st) {
   return MC_E_UNSUPPORTED;
 }
 
+#endif
+#if MC_TA_PART != 1
 static int dispatch_bwd(TAParams& prm, int L, int DH, cudaStream_t st) {
   if (L == 8) { MC_DISPATCH_DH(8, launch_bwd) }
   if (L == 16) { MC_DISPATCH_DH(16, launch_bwd) }
@@ -988,8 +997,10 @@ static int dispatch_bwd(TAParams& prm, int L, int DH, cudaStream_t st) {
   return MC_E_UNSUPPORTED;
 }
 
+#endif
 }  // namespace mc
 
+#if MC_TA_PART != 2
 extern "C" int mc_temporal_attn_fwd(const void* q, const void* k, const void* v, mc_temporal_layout qkv_layout,
                                     void* o, mc_temporal_layout o_layout, void* probs, void* top_val,
                                     uint8_t* top_idx, const uint8_t* gather_idx, void* gathered, int B, int D, int L,
@@ -1026,6 +1037,8 @@ extern "C" int mc_temporal_attn_fwd(const void* q, const void* k, const void* v,
   return dispatch_fwd(prm, L, DH, (cudaStream_t)stream);
 }
 
+#endif
+#if MC_TA_PART != 1
 extern "C" int mc_temporal_attn_bwd(const void* q, const void* k, const void* v, mc_temporal_layout qkv_layout,
                                     const void* d_o, mc_temporal_layout do_layout, const void* d_probs,
                                     const uint8_t* gather_idx, const void* d_gathered, void* dq, void* dk, void* dv,
@@ -1064,3 +1077,4 @@ extern "C" int mc_temporal_attn_bwd(const void* q, const void* k, const void* v,
   prm.scale = scale;
   return dispatch_bwd(prm, L, DH, (cudaStream_t)stream);
 }
+#endif
