@@ -1,6 +1,6 @@
 """Generates tests/golden/*.npz by running the UNMODIFIED reference (oracle/ref_runner.py). TEST INFRASTRUCTURE.
 
-Run in the build container only:  python oracle/gen_golden.py [tiny8 tiny16 c1]
+Run in the build container only:  python oracle/gen_golden.py [tiny8 tiny16 c1 c2mini ...]
 The fixtures are committed; the GPU box never needs /root/reference.
 """
 import json
@@ -34,6 +34,10 @@ CASES = {
     # BASELINE.json configs[0]: t2v_camera, 8x256x256, 10 DDIM steps, SD1.5 widths (plumbing case, CPU-runnable)
     "c1": ("sd15", dict(BASE, inference_steps=10, guidance_steps=5, guidance_scale=0.3, video_length=8, height=256,
                         width=256), 42),
+    # BASELINE.json configs[1] topology (t2v_object: 16 frames, SD1.5 + motion-module widths, guidance_scale 0.4) at 128x128
+    # pixels and 4 DDIM steps: the head dims (40 / 80 / 160) and the frame count the bench config runs, CPU-runnable
+    "c2mini": ("sd15", dict(BASE, inference_steps=4, guidance_steps=2, guidance_scale=0.4, video_length=16, height=128,
+                            width=128, warm_up_steps=2, cool_up_steps=2), 82),
 }
 
 
@@ -79,7 +83,7 @@ def main(names):
         path = os.path.join(ROOT, "tests", "golden", f"ref_{name}.npz")
         np.savez_compressed(path, **arrays)
         print(name, "->", path, os.path.getsize(path) // 1024, "KiB", round(time.time() - t0, 1), "s", flush=True)
-        if name != "c1":
+        if ucfg_name == "tiny":
             shapes = {k: list(v.shape) for k, v in pipe.unet.state_dict().items()}
             with open(os.path.join(ROOT, "tests", "golden", f"ref_state_dict_shapes_{ucfg_name}.json"), "w") as f:
                 json.dump(shapes, f, indent=0)

@@ -63,17 +63,23 @@ def test_guided_sampling_loop_tiny8():
         list(g["timesteps"])
 
 
-def test_c1_fixture_present_and_consistent():
-    """BASELINE.json configs[0] (8x256x256, 10 steps, SD1.5 widths) was run through the reference once; the oracle
-    cannot redo it in seconds, so only the fixture's own consistency is checked here (the GPU test consumes it)."""
-    path = os.path.join(GOLDEN, "ref_c1.npz")
+@pytest.mark.parametrize("case,steps,guided,gs,frames", [("c1", 10, 5, 0.3, 8), ("c2mini", 4, 2, 0.4, 16)])
+def test_sd15_width_fixtures_present_and_consistent(case, steps, guided, gs, frames):
+    """BASELINE.json configs[0] (c1: 8x256x256, 10 steps) and the configs[1] topology at reduced resolution (c2mini:
+    16 frames, 128x128, 4 steps), both at the full SD1.5 + motion-module widths, were run through the reference once;
+    the oracle cannot redo them in seconds, so only the fixtures' own consistency is checked here (the GPU tests consume
+    them)."""
+    path = os.path.join(GOLDEN, f"ref_{case}.npz")
     if not os.path.exists(path):
-        pytest.skip("ref_c1.npz not generated")
+        pytest.skip(f"ref_{case}.npz not generated")
     g = np.load(path)
     meta = json.loads(str(g["meta"]))
-    assert meta["infer"]["inference_steps"] == 10 and meta["unet"] == "sd15"
-    assert list(g["timesteps"]) == list(O.uneven_timesteps(10, 5, 0.3)) == [999, 924, 850, 775, 700, 699, 524, 350, 175, 0]
-    assert np.isfinite(g["latents_per_step"]).all()
+    assert meta["infer"]["inference_steps"] == steps and meta["unet"] == "sd15" and meta["infer"]["video_length"] == frames
+    assert list(g["timesteps"]) == list(O.uneven_timesteps(steps, guided, gs))
+    if case == "c1":
+        assert list(g["timesteps"]) == [999, 924, 850, 775, 700, 699, 524, 350, 175, 0]
+    assert np.isfinite(g["latents_per_step"]).all() and np.isfinite(g["grad_step_0"]).all()
+    assert g["repr_idx_0"].dtype == np.uint8 and g["repr_idx_0"].max() < frames and g["repr_idx_0"].shape[2] == frames
 
 
 @pytest.mark.parametrize("case", ["tiny8_i2v_latent", "tiny8_i2v_image"])

@@ -66,7 +66,7 @@ def _oracle_controlnet(run_or_pipe, meta, inp, dev):
                 scale=meta["infer"]["controlnet_scale"], images=inp["controlnet_images"].to(dev, torch.float16))
 
 
-@pytest.fixture(scope="module", params=["tiny8", "tiny16", "c1", "tiny8_i2v_latent", "tiny8_i2v_image"])
+@pytest.fixture(scope="module", params=["tiny8", "tiny16", "c1", "tiny8_i2v_latent", "tiny8_i2v_image", "c2mini"])
 def run(request):
     assert torch.cuda.is_available()
     dev = torch.device("cuda:0")
