@@ -143,6 +143,21 @@ int mc_self_attn_short_fwd(const void* q, const void* k, const void* v, void* o,
                            int64_t qkv_stride_b, int64_t qkv_stride_row, int64_t o_stride_b, int64_t o_stride_row,
                            float scale, void* stream);
 
+/*
+ * Spatial self-attention on tcgen05 tensor cores with TMEM accumulators and tensor-map TMA operand loads
+ * (csrc/spatial_attn_tc.cu): O = softmax(scale * Q K^T) V per (frame, head) over the N tokens of one frame, any N >= 1
+ * (128-key tiles, online softmax). Replaces the xformers call for `attn1`
+ * (models/attention.py:190-192, :271-278 -> :535-542, xformers.ops.memory_efficient_attention, attn_bias=None).
+ * q, k, v, o: [B, N, H*DH] views with their own frame / token strides in elements (multiples of 8; 16-byte aligned
+ * pointers), head h in columns [h*DH, (h+1)*DH) - e.g. the column blocks of one fused QKV projection.
+ * lse (nullable): fp32 [B, H, N], natural-log sum-exp of the scaled scores, kept for the backward.
+ * DH in {8, 16, 32, 40, 64, 80, 160}.
+ */
+int mc_spatial_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int N, int H, int DH,
+                        int64_t q_stride_b, int64_t q_stride_row, int64_t k_stride_b, int64_t k_stride_row,
+                        int64_t v_stride_b, int64_t v_stride_row, int64_t o_stride_b, int64_t o_stride_row, float scale,
+                        void* stream);
+
 /* out = a + bias[c] + b on channel-innermost fp16 tensors (n elements, C channels): the resnet's residual add
  * `input_tensor + hidden_states` (models/resnet.py:209-211) with conv2's (+ the shortcut conv's) bias folded in. */
 int mc_bias_residual_add(const void* a, const void* b, const void* bias, void* out, int64_t n, int C, void* stream);

@@ -1,0 +1,354 @@
+// Spatial self-attention (S1) on 5th-gen tensor cores: tcgen05.mma with TMEM accumulators, operands staged by tensor-map
+// TMA (cp.async.bulk.tensor), sm_100a. Forward (this file, part 1) and backward (part 2: dQ kernel, dK/dV kernel).
+//
+// Replaces the xformers seam of `attn1` (reference models/attention.py:190-192, :271-278 -> :535-542,
+// xformers.ops.memory_efficient_attention(q, k, v, attn_bias=None)): O = softmax(scale Q K^T) V per (frame, head) over the
+// N = h*w tokens of one frame; N = 4096 / 1024 / 256 / 64 and DH = 40 / 80 / 160 / 160 at 16 x 512 x 512. fp32 softmax
+// statistics, one rounding of the output (xformers / flash semantics - SURVEY.md appendix "Attention numerics").
+//
+// Forward, one CTA = one (frame, head, 128-query tile); 160 threads = 4 softmax warps (thread r owns query row r = TMEM
+// lane r) + 1 producer warp whose lane 0 issues every TMA load and every MMA. Two CTAs share an SM (TMEM 2 x 256 columns),
+// so one CTA's exponentials overlap the other's MMAs. Per 128-key tile j:
+//   producer:  S = Q K_j^T           tcgen05.mma M=128 N=128 K=DH -> TMEM columns [0,128)          -> commit s_full
+//   softmax :  S -> registers (128 fp32 per thread), release S (s_free: the producer may issue S_{j+1} at once),
+//              row max / exp2 / row sum, P -> fp16 -> shared memory (K-major SW128)                -> arrive p_full
+//   producer:  O += P V_j            tcgen05.mma M=128 N=DH K=128 (V MN-major: no transpose)       -> commit pv_done
+// O stays in TMEM for the whole key loop. The running maximum is only raised when a row's maximum grows by more than
+// 2^8 (P <= 256 fits fp16; exactness is unaffected because the row sum uses the same reference maximum); only then does
+// the softmax warp rescale its 32 rows of O in TMEM (tcgen05.ld -> multiply -> tcgen05.st) before releasing P.
+// K and V are single-buffered: K_{j+1} is requested the moment S_j has completed and V_{j+1} when P V_j has - both land
+// long before the exp-bound softmax of tile j (>= 1024 cycles: 16 384 exponentials at 16 / cycle / SM) is through.
+#include <math.h>
+
+#include "tma_common.cuh"
+
+namespace mc {
+
+constexpr int kFM = 128;         // query rows per CTA (UMMA M)
+constexpr int kFN = 128;         // keys per tile (UMMA N of S, K extent of P V)
+constexpr int kFThreads = 160;   // 4 softmax warps + 1 producer warp
+constexpr float kRescaleThreshold = 8.f;  // log2 units
+
+struct FAParams {
+  float* lse;        // [B][H][N] natural-log sum-exp of the scaled scores (nullable)
+  __half* o;
+  int64_t o_sb, o_sr;
+  int B, N, H;
+  float scale_log2e;  // scale * log2(e)
+};
+
+template <int DH>
+struct FACfg {
+  using T = TileParts<DH>;
+  static constexpr int DHP = T::DHP;
+  static constexpr int P_BYTES = 2 * 16384;                 // P [128 q][128 keys] fp16: two K-major SW128 parts
+  static constexpr int OFF_Q = 0, OFF_K = T::BYTES, OFF_V = 2 * T::BYTES, OFF_P = 3 * T::BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int SMEM = OFF_BAR + 128 + 1024;          // + alignment slack (dynamic smem base is 16 B aligned)
+  static constexpr int O_COL = 128;                          // O at TMEM columns [128, 128 + DHP)
+  static constexpr int TCOLS = (128 + DHP <= 256) ? 256 : 512;
+  static constexpr int CTAS_PER_SM = (TCOLS == 256 && 2 * SMEM <= 227 * 1024) ? 2 : 1;
+};
+
+// S tile: A = Q (K-major), B = K (K-major); one MMA per k16 step over the head dim
+template <int DH>
+__device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint32_t sA, uint32_t sB, int n_rows_b = kFN) {
+  using T = TileParts<DH>;
+  const uint32_t idesc = umma_idesc_f16(kFM, n_rows_b, false, false);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int p = 0; p < T::N64; ++p)
+#pragma unroll
+    for (int ks = 0; ks < T::KS64; ++ks) {
+      umma_f16(d_tmem, desc_k128(sA + T::part64_off(p), ks), desc_k128(sB + T::part64_off(p), ks), idesc, acc);
+      acc = 1;
+    }
+#pragma unroll
+  for (int p = 0; p < T::N16; ++p) {
+    umma_f16(d_tmem, desc_k32(sA + T::part16_off(p)), desc_k32(sB + T::part16_off(p)), idesc, acc);
+    acc = 1;
+  }
+}
+
+// D[128 x DH] (+)= A[128 x 128] B[128 x DH]: A = two K-major SW128 parts written by threads (P or dS, K = 128 rows of B),
+// B = an operand tile read MN-major (its rows are the K dimension). One MMA per (k16 step, part of B).
+template <int DH>
+__device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t sA, uint32_t sB, bool accumulate, int ksteps = kFN / 16) {
+  using T = TileParts<DH>;
+  const uint32_t idesc64 = umma_idesc_f16(kFM, T::W64, false, true);
+  const uint32_t idesc16 = umma_idesc_f16(kFM, 16, false, true);
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint64_t a = desc_k128(sA + (ks >> 2) * 16384, ks & 3);
+    const uint32_t acc = (accumulate || ks > 0) ? 1u : 0u;
+#pragma unroll
+    for (int p = 0; p < T::N64; ++p) umma_f16(d_tmem + p * 64, a, desc_mn128(sB + T::part64_off(p), ks), idesc64, acc);
+#pragma unroll
+    for (int p = 0; p < T::N16; ++p)
+      umma_f16(d_tmem + T::N64 * 64 + p * 16, a, desc_mn32(sB + T::part16_off(p), ks), idesc16, acc);
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(kFThreads, FACfg<DH>::CTAS_PER_SM)
+spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_constant__ CUtensorMap mk128,
+                        const __grid_constant__ CUtensorMap mv128, const __grid_constant__ CUtensorMap mq32,
+                        const __grid_constant__ CUtensorMap mk32, const __grid_constant__ CUtensorMap mv32,
+                        const FAParams prm) {
+  using X = FACfg<DH>;
+  using T = TileParts<DH>;
+  constexpr int DHP = X::DHP;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem + X::OFF_Q;
+  uint8_t* sK = smem + X::OFF_K;
+  uint8_t* sV = smem + X::OFF_V;
+  uint8_t* sP = smem + X::OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X::OFF_BAR);
+  uint64_t* bar_q = bars + 0;      // Q landed                       (tx)
+  uint64_t* bar_k = bars + 1;      // K_j landed                     (tx, phase j & 1)
+  uint64_t* bar_v = bars + 2;      // V_j landed                     (tx)
+  uint64_t* s_full = bars + 3;     // S_j in TMEM                    (tcgen05.commit)
+  uint64_t* s_free = bars + 4;     // S_j copied to registers        (4 warp arrivals)
+  uint64_t* p_full = bars + 5;     // P_j in shared memory           (4 warp arrivals)
+  uint64_t* pv_done = bars + 6;    // O += P_j V_j completed         (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * kFM, N = prm.N;
+  const int T_tiles = (N + kFN - 1) / kFN;
+
+  if (warp == 4) {
+    tmem_alloc<X::TCOLS>(tmem_slot);
+    if (lane == 0) {
+      mbar_init(bar_q, 1), mbar_init(bar_k, 1), mbar_init(bar_v, 1), mbar_init(s_full, 1);
+      mbar_init(s_free, 4), mbar_init(p_full, 4), mbar_init(pv_done, 1);
+      fence_mbar_init();
+      tma_prefetch_desc(&mq128), tma_prefetch_desc(&mk128), tma_prefetch_desc(&mv128);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ================= producer: TMA + MMA issue (one thread) =================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q, T::BYTES);
+      tma_load_tile<DH>(sQ, &mq128, &mq32, bar_q, q0, h, b);
+      mbar_arrive_expect_tx(bar_k, T::BYTES);
+      tma_load_tile<DH>(sK, &mk128, &mk32, bar_k, 0, h, b);
+      mbar_arrive_expect_tx(bar_v, T::BYTES);
+      tma_load_tile<DH>(sV, &mv128, &mv32, bar_v, 0, h, b);
+      mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, 0);
+      tc_fence_after();
+      issue_qk<DH>(tmem_base, smem_u32(sQ), smem_u32(sK));
+      umma_commit(s_full);
+      for (int j = 0; j < T_tiles; ++j) {
+        const uint32_t ph = j & 1;
+        mbar_wait(s_full, ph);  // S_j completed: the K buffer is free
+        if (j + 1 < T_tiles) {
+          mbar_arrive_expect_tx(bar_k, T::BYTES);
+          tma_load_tile<DH>(sK, &mk128, &mk32, bar_k, (j + 1) * kFN, h, b);
+          mbar_wait(bar_k, ph ^ 1);
+          mbar_wait(s_free, ph);  // every softmax thread holds S_j in registers
+          tc_fence_after();
+          issue_qk<DH>(tmem_base, smem_u32(sQ), smem_u32(sK));
+          umma_commit(s_full);
+        }
+        mbar_wait(bar_v, ph);
+        mbar_wait(p_full, ph);
+        tc_fence_after();
+        issue_pv<DH>(tmem_base + X::O_COL, smem_u32(sP), smem_u32(sV), j > 0);
+        umma_commit(pv_done);
+        if (j + 1 < T_tiles) {
+          mbar_wait(pv_done, ph);  // V buffer (and P buffer) free
+          mbar_arrive_expect_tx(bar_v, T::BYTES);
+          tma_load_tile<DH>(sV, &mv128, &mv32, bar_v, (j + 1) * kFN, h, b);
+        }
+      }
+    }
+  } else {
+    // ================= softmax warps: thread = query row =================
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float c = prm.scale_log2e;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < T_tiles; ++j) {
+      const uint32_t ph = j & 1;
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      uint32_t s[kFN];
+      tmem_ld32(lane_addr + 0, s + 0);
+      tmem_ld32(lane_addr + 32, s + 32);
+      tmem_ld32(lane_addr + 64, s + 64);
+      tmem_ld32(lane_addr + 96, s + 96);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+
+      const int kvalid = N - j * kFN;  // keys of this tile that exist (>= 1)
+      if (kvalid < kFN) {
+#pragma unroll
+        for (int i = 0; i < kFN; ++i)
+          if (i >= kvalid) s[i] = 0xff800000u;  // -inf
+      }
+      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
+            mx3 = __uint_as_float(s[3]);
+#pragma unroll
+      for (int i = 4; i < kFN; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[i])), mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2])), mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+      }
+      const float mxc = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+      bool waited_pv = false;
+      if (j == 0) {
+        m_used = mxc;
+      } else {
+        const bool grow = mxc - m_used > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = grow ? mxc : m_used;
+          const float alpha = ex2_approx(m_used - m_new);
+          l *= alpha;
+          m_used = m_new;
+          mbar_wait(pv_done, ph ^ 1);  // O holds tiles 0..j-1
+          waited_pv = true;
+          tc_fence_after();
+#pragma unroll
+          for (int cc = 0; cc < DHP / 16; ++cc) {
+            uint32_t r[16];
+            tmem_ld16(lane_addr + X::O_COL + cc * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st16(lane_addr + X::O_COL + cc * 16, r);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+      }
+      // p = exp2(s*c - m_used); packed to fp16 pairs in place (s[0..63] hold the 128 probabilities)
+      const float negm = -m_used;
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < kFN; i += 2) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), c, negm));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), c, negm));
+        l0 += p0, l1 += p1;
+        s[i >> 1] = pack_half2(p0, p1);
+      }
+      l += l0 + l1;
+      if (j > 0 && !waited_pv) mbar_wait(pv_done, ph ^ 1);  // P_{j-1} consumed: the P buffer is free
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) {  // 16-byte chunk ch = keys [8 ch, 8 ch + 8)
+        uint8_t* dst = sP + (ch >> 3) * 16384 + sw128_chunk_off(tid, ch & 7);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(s[4 * ch], s[4 * ch + 1], s[4 * ch + 2], s[4 * ch + 3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> fp16 -> global; log-sum-exp for the backward ----
+    mbar_wait(pv_done, (T_tiles - 1) & 1);
+    tc_fence_after();
+    const int row = q0 + tid;
+    const float inv = 1.f / l;
+    __half* orow = prm.o + (int64_t)b * prm.o_sb + (int64_t)row * prm.o_sr + h * DH;
+#pragma unroll
+    for (int cc = 0; cc < DHP / 16; ++cc) {
+      uint32_t r[16];
+      tmem_ld16(lane_addr + X::O_COL + cc * 16, r);
+      tmem_ld_wait();
+      if (row < N) {
+#pragma unroll
+        for (int half8 = 0; half8 < 2; ++half8) {
+          if (cc * 16 + half8 * 8 < DH) {
+            uint4 pk;
+            pk.x = pack_half2(__uint_as_float(r[half8 * 8 + 0]) * inv, __uint_as_float(r[half8 * 8 + 1]) * inv);
+            pk.y = pack_half2(__uint_as_float(r[half8 * 8 + 2]) * inv, __uint_as_float(r[half8 * 8 + 3]) * inv);
+            pk.z = pack_half2(__uint_as_float(r[half8 * 8 + 4]) * inv, __uint_as_float(r[half8 * 8 + 5]) * inv);
+            pk.w = pack_half2(__uint_as_float(r[half8 * 8 + 6]) * inv, __uint_as_float(r[half8 * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + cc * 16 + half8 * 8) = pk;
+          }
+        }
+      }
+    }
+    if (prm.lse != nullptr && row < N)
+      prm.lse[((int64_t)b * prm.H + h) * N + row] = (m_used + log2f(l)) * 0.6931471805599453f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<X::TCOLS>(tmem_base);
+}
+
+struct AttnMaps {
+  CUtensorMap m128, m32;
+};
+
+// maps for one operand tensor; the SW32 map is only encoded when the head dim has 16-wide parts
+template <int DH>
+static int make_maps(AttnMaps& m, const void* base, int H, int N, int B, int64_t sr, int64_t sb) {
+  using T = TileParts<DH>;
+  int rc = make_attn_tensor_map(&m.m128, base, DH, H, N, B, sr, sb, 64, 128, true);
+  if (rc) return rc;
+  if (T::N16 > 0) rc = make_attn_tensor_map(&m.m32, base, DH, H, N, B, sr, sb, 16, 128, false);
+  else m.m32 = m.m128;
+  return rc;
+}
+
+template <int DH>
+static int launch_spatial_fwd(const void* q, const void* k, const void* v, const FAParams& prm, int64_t q_sb, int64_t q_sr,
+                              int64_t k_sb, int64_t k_sr, int64_t v_sb, int64_t v_sr, cudaStream_t st) {
+  using X = FACfg<DH>;
+  AttnMaps mq, mk, mv;
+  if (make_maps<DH>(mq, q, prm.H, prm.N, prm.B, q_sr, q_sb) || make_maps<DH>(mk, k, prm.H, prm.N, prm.B, k_sr, k_sb) ||
+      make_maps<DH>(mv, v, prm.H, prm.N, prm.B, v_sr, v_sb)) {
+    set_error("spatial_attn_fwd: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned, strides multiples of 8)");
+    return MC_E_CUDA;
+  }
+  auto kern = spatial_attn_fwd_kernel<DH>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, X::SMEM);
+  dim3 grid((prm.N + kFM - 1) / kFM, prm.H, prm.B);
+  kern<<<grid, kFThreads, X::SMEM, st>>>(mq.m128, mk.m128, mv.m128, mq.m32, mk.m32, mv.m32, prm);
+  count_launch();
+  return check_launch("spatial_attn_fwd");
+}
+
+}  // namespace mc
+
+extern "C" int mc_spatial_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int N, int H,
+                                   int DH, int64_t q_stride_b, int64_t q_stride_row, int64_t k_stride_b,
+                                   int64_t k_stride_row, int64_t v_stride_b, int64_t v_stride_row, int64_t o_stride_b,
+                                   int64_t o_stride_row, float scale, void* stream) {
+  using namespace mc;
+  if (!q || !k || !v || !o || B <= 0 || N <= 0 || H <= 0) {
+    set_error("spatial_attn_fwd: null pointer or non-positive dims");
+    return MC_E_INVALID;
+  }
+  if (B > 65535 || H > 65535) {
+    set_error("spatial_attn_fwd: at most 65535 frames / heads");
+    return MC_E_UNSUPPORTED;
+  }
+  if ((q_stride_b | q_stride_row | k_stride_b | k_stride_row | v_stride_b | v_stride_row | o_stride_b | o_stride_row) % 8 ||
+      ((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) % 16) {
+    set_error("spatial_attn_fwd: pointers must be 16-byte aligned and strides multiples of 8 elements");
+    return MC_E_INVALID;
+  }
+  FAParams prm{};
+  prm.lse = lse, prm.o = (__half*)o, prm.o_sb = o_stride_b, prm.o_sr = o_stride_row;
+  prm.B = B, prm.N = N, prm.H = H;
+  prm.scale_log2e = scale * 1.44269504088896340736f;
+  cudaStream_t st = (cudaStream_t)stream;
+#define MC_SA_CASE(D) \
+  case D: return launch_spatial_fwd<D>(q, k, v, prm, q_stride_b, q_stride_row, k_stride_b, k_stride_row, v_stride_b, v_stride_row, st);
+  switch (DH) {
+    MC_SA_CASE(8) MC_SA_CASE(16) MC_SA_CASE(32) MC_SA_CASE(40) MC_SA_CASE(64) MC_SA_CASE(80) MC_SA_CASE(160)
+    default: break;
+  }
+#undef MC_SA_CASE
+  set_error("spatial_attn_fwd: unsupported head dim %d (8, 16, 32, 40, 64, 80, 160)", DH);
+  return MC_E_UNSUPPORTED;
+}

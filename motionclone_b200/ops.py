@@ -574,3 +574,39 @@ def self_attention_short(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: flo
     if ev0 is not None:  # Q, K, V read + O written
         TIMER.stop("self_attn_short_fwd", 4 * B * N * C * 2, ev0)
     return o
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# spatial self-attention (tcgen05 + tensor-map TMA flash kernel, csrc/spatial_attn_tc.cu)
+# ----------------------------------------------------------------------------------------------------------------
+SPATIAL_ATTN_HEAD_DIMS = (8, 16, 32, 40, 64, 80, 160)
+
+
+def _check_bnc(name: str, t: Tensor) -> None:
+    _require(t, name)
+    if t.dim() != 3 or t.stride(2) != 1 or t.stride(0) % 8 or t.stride(1) % 8 or t.data_ptr() % 16:
+        raise ValueError(f"{name} must be a [B, N, C] view with contiguous channels, strides that are multiples of 8 "
+                         "elements and a 16-byte aligned base")
+
+
+def spatial_attention_forward(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float, want_lse: bool = False):
+    """q, k, v: [B, N, C] views (any frame / token strides, e.g. column blocks of a fused QKV projection).
+    -> (o [B, N, C] contiguous, lse [B, H, N] fp32 | None). attention.py:535-542 semantics."""
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        _check_bnc(name, t)
+        if t.shape != q.shape:
+            raise ValueError("q, k, v must share one shape")
+    B, N, C = q.shape
+    if C % heads or (C // heads) not in SPATIAL_ATTN_HEAD_DIMS:
+        raise NotImplementedError(f"spatial attention: head dim {C // heads if C % heads == 0 else '?'} not in "
+                                  f"{SPATIAL_ATTN_HEAD_DIMS}")
+    o = torch.empty((B, N, C), dtype=q.dtype, device=q.device)
+    lse = torch.empty((B, heads, N), dtype=torch.float32, device=q.device) if want_lse else None
+    ev0 = TIMER.start() if TIMER is not None else None
+    st = _lib.lib().mc_spatial_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), B, N, heads, C // heads,
+                                        q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                                        o.stride(0), o.stride(1), float(scale), _stream())
+    _lib.check(st, "mc_spatial_attn_fwd")
+    if ev0 is not None:  # flops: 4 B N^2 C (QK^T + PV); reported as the tensor-bound kernel of the path
+        TIMER.stop("spatial_attn_fwd", 4 * B * N * N * C, ev0)
+    return o, lse
