@@ -158,6 +158,22 @@ int mc_spatial_attn_fwd(const void* q, const void* k, const void* v, void* o, fl
                         int64_t v_stride_b, int64_t v_stride_row, int64_t o_stride_b, int64_t o_stride_row, float scale,
                         void* stream);
 
+/*
+ * Backward of mc_spatial_attn_fwd w.r.t. q, k, v (the autograd of the xformers seam that torch.autograd.grad traverses,
+ * utils/motionclone_functions.py:236): dV = P^T dO, dS = scale * P o (dO V^T - rowsum(dO o O)), dQ = dS K, dK = dS^T Q,
+ * with P recomputed from the forward's log-sum-exp `lse` [B, H, N]. Three launches: rowsum(dO o O) -> workspace, a dQ
+ * kernel (128-query CTAs streaming 64-key tiles) and a dK/dV kernel (128-key CTAs streaming 64-query tiles); tcgen05 +
+ * TMEM + tensor-map TMA throughout, no atomics (deterministic). o, d_o: [B, N, H*DH] with their own strides; dq, dk, dv
+ * share g_stride_* (e.g. the column blocks of one fused [B, N, 3*H*DH] gradient buffer).
+ * workspace: mc_spatial_attn_bwd_workspace_bytes(B, N, H) bytes of device memory (fp32 [B, H, N]).
+ */
+int64_t mc_spatial_attn_bwd_workspace_bytes(int B, int N, int H);
+int mc_spatial_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                        void* dq, void* dk, void* dv, void* workspace, int B, int N, int H, int DH, int64_t q_stride_b,
+                        int64_t q_stride_row, int64_t k_stride_b, int64_t k_stride_row, int64_t v_stride_b,
+                        int64_t v_stride_row, int64_t o_stride_b, int64_t o_stride_row, int64_t do_stride_b,
+                        int64_t do_stride_row, int64_t g_stride_b, int64_t g_stride_row, float scale, void* stream);
+
 /* out = a + bias[c] + b on channel-innermost fp16 tensors (n elements, C channels): the resnet's residual add
  * `input_tensor + hidden_states` (models/resnet.py:209-211) with conv2's (+ the shortcut conv's) bias folded in. */
 int mc_bias_residual_add(const void* a, const void* b, const void* bias, void* out, int64_t n, int C, void* stream);

@@ -64,9 +64,10 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 }
 
 // ---- operand-tile geometry ----
-template <int DH>
+template <int DH, int ROWS = 128>
 struct TileParts {
   static_assert(DH % 8 == 0, "head dim must be a multiple of 8 (16-byte rows)");
+  static_assert(ROWS % 8 == 0 && ROWS <= 256, "tile rows");
   static constexpr int N64 = DH >= 64 ? DH / 64 : 1;   // SW128 parts
   static constexpr int REM = DH >= 64 ? DH % 64 : 0;
   static_assert(REM % 16 == 0, "head dims above 64 must be 64*a + 16*b");
@@ -74,17 +75,19 @@ struct TileParts {
   static constexpr int DHP = DH >= 64 ? DH : (DH + 15) / 16 * 16;  // extent seen by the MMA (zero-padded below 64)
   static constexpr int KS64 = DH >= 64 ? 4 : DHP / 16;             // k16 steps per SW128 part when DH is the K dim
   static constexpr int W64 = DH >= 64 ? 64 : DHP;                  // N extent per SW128 part when DH is the N dim
-  static constexpr int BYTES = N64 * 16384 + N16 * 4096;
+  static constexpr int P64 = ROWS * 128, P16 = ROWS * 32;          // bytes per part
+  static constexpr int BYTES = N64 * P64 + N16 * P16;
   static constexpr int KSTEPS = N64 * KS64 + N16;
-  __host__ __device__ static constexpr int part64_off(int p) { return p * 16384; }
-  __host__ __device__ static constexpr int part16_off(int p) { return N64 * 16384 + p * 4096; }
+  __host__ __device__ static constexpr int part64_off(int p) { return p * P64; }
+  __host__ __device__ static constexpr int part16_off(int p) { return N64 * P64 + p * P16; }
 };
 
-// one thread: issue the loads of one [128 rows][DH] tile (rows r0.. of head h, frame b); bytes = TileParts<DH>::BYTES
-template <int DH>
+// one thread: issue the loads of one [ROWS][DH] tile (rows r0.. of head h, frame b); bytes = TileParts<DH, ROWS>::BYTES.
+// The maps' box height must be ROWS.
+template <int DH, int ROWS = 128>
 __device__ __forceinline__ void tma_load_tile(uint8_t* sdst, const CUtensorMap* map128, const CUtensorMap* map32,
                                               uint64_t* bar, int r0, int h, int b) {
-  using T = TileParts<DH>;
+  using T = TileParts<DH, ROWS>;
 #pragma unroll
   for (int p = 0; p < T::N64; ++p) tma_load_4d(sdst + T::part64_off(p), map128, bar, p * 64, h, r0, b);
 #pragma unroll

@@ -610,3 +610,69 @@ def spatial_attention_forward(q: Tensor, k: Tensor, v: Tensor, heads: int, scale
     if ev0 is not None:  # flops: 4 B N^2 C (QK^T + PV); reported as the tensor-bound kernel of the path
         TIMER.stop("spatial_attn_fwd", 4 * B * N * N * C, ev0)
     return o, lse
+
+
+def spatial_attention_backward(q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, d_o: Tensor, heads: int,
+                               scale: float) -> Tensor:
+    """-> dqkv [B, N, 3C]: the gradients w.r.t. q, k, v as the column blocks of ONE buffer (the gradient of the fused
+    QKV projection output, no concatenation)."""
+    for name, t in (("q", q), ("k", k), ("v", v), ("o", o)):
+        _check_bnc(name, t)
+    _require(d_o, "d_o")
+    if d_o.dim() != 3 or d_o.stride(2) != 1 or d_o.stride(0) % 8 or d_o.stride(1) % 8 or d_o.data_ptr() % 16:
+        d_o = d_o.contiguous()
+    _require(lse, "lse", torch.float32)
+    B, N, C = q.shape
+    dqkv = torch.empty((B, N, 3 * C), dtype=q.dtype, device=q.device)
+    ws = torch.empty((B, heads, N), dtype=torch.float32, device=q.device)
+    ev0 = TIMER.start() if TIMER is not None else None
+    st = _lib.lib().mc_spatial_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(d_o), _ptr(lse),
+                                        ctypes.c_void_p(dqkv.data_ptr()), ctypes.c_void_p(dqkv.data_ptr() + 2 * C),
+                                        ctypes.c_void_p(dqkv.data_ptr() + 4 * C), _ptr(ws), B, N, heads, C // heads,
+                                        q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                                        o.stride(0), o.stride(1), d_o.stride(0), d_o.stride(1), dqkv.stride(0),
+                                        dqkv.stride(1), float(scale), _stream())
+    _lib.check(st, "mc_spatial_attn_bwd")
+    if ev0 is not None:  # flops as launched: 7 GEMMs of 2 B N^2 C (S and dP are computed in both kernels)
+        TIMER.stop("spatial_attn_bwd", 14 * B * N * N * C, ev0)
+    return dqkv
+
+
+class SpatialAttentionTC(torch.autograd.Function):
+    """O = softmax(scale Q K^T) V per (frame, head) on the tcgen05 kernels, forward and backward.
+    q, k, v: [B, N, C] views; when they are the column blocks of one fused [B, N, 3C] tensor autograd accumulates the
+    three returned gradient views into that tensor's gradient."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads, scale):
+        o, lse = spatial_attention_forward(q, k, v, heads, scale, want_lse=True)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.heads, ctx.scale = heads, scale
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, k, v, o, lse = ctx.saved_tensors
+        C = q.shape[-1]
+        dqkv = spatial_attention_backward(q, k, v, o, lse, d_o, ctx.heads, ctx.scale)
+        return dqkv[..., :C], dqkv[..., C:2 * C], dqkv[..., 2 * C:], None, None
+
+
+class SpatialAttentionFusedTC(torch.autograd.Function):
+    """Same, on a fused projection output qkv [B, N, 3C]: one gradient tensor comes back (no view accumulation)."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, scale):
+        C = qkv.shape[-1] // 3
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        o, lse = spatial_attention_forward(q, k, v, heads, scale, want_lse=True)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.heads, ctx.scale = heads, scale
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, o, lse = ctx.saved_tensors
+        C = qkv.shape[-1] // 3
+        return spatial_attention_backward(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], o, lse, d_o, ctx.heads,
+                                          ctx.scale), None, None

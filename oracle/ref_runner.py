@@ -165,6 +165,9 @@ def run_reference(unet_config: dict, infer_cfg: dict, inputs: dict, repr_path: s
     rep = torch.load(repr_path)
     probs = pipeline.get_temp_attn_prob()  # processors still hold the extraction pass's q,k
     out["extract_probs_0"] = next(iter(probs.values())).float().cpu()
+    for i, pr in enumerate(probs.values()):  # top-1 minus top-2 probability of every guided module's rows: an index
+        top2 = pr.float().topk(2, dim=-1).values   # mismatch is only acceptable where the REFERENCE's own row is a near-tie
+        out[f"extract_top2gap_{i}"] = (top2[..., 0] - top2[..., 1]).cpu()
     out["repr_names"] = list(rep.keys())
     for i, (k, (val, idx)) in enumerate(rep.items()):
         out[f"repr_val_{i}"] = val.float().cpu()
