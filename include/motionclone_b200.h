@@ -133,17 +133,6 @@ int mc_cross_attn_bwd_dq(const void* q, const void* k, const void* v, const void
                          int64_t dq_stride_row, float scale, void* stream);
 
 /*
- * Spatial self-attention for short sequences on tcgen05 / TMEM (csrc/self_attn_tc.cu): O = softmax(scale * Q K^T) V per
- * (frame, head) with N <= 256 tokens per frame — the whole key axis is one TMEM tile. Replaces the xformers call for
- * `attn1` (models/attention.py:190-192, :271-278 -> :535-542) at the 16x16 and 8x8 latent levels in the inference
- * passes. q, k, v: [B, N, H*DH] views sharing one stride pattern (e.g. column blocks of a fused QKV projection);
- * strides in elements (multiples of 8); DH in {40, 64, 80, 160}.
- */
-int mc_self_attn_short_fwd(const void* q, const void* k, const void* v, void* o, int B, int N, int H, int DH,
-                           int64_t qkv_stride_b, int64_t qkv_stride_row, int64_t o_stride_b, int64_t o_stride_row,
-                           float scale, void* stream);
-
-/*
  * Spatial self-attention on tcgen05 tensor cores with TMEM accumulators and tensor-map TMA operand loads
  * (csrc/spatial_attn_tc.cu): O = softmax(scale * Q K^T) V per (frame, head) over the N tokens of one frame, any N >= 1
  * (128-key tiles, online softmax). Replaces the xformers call for `attn1`

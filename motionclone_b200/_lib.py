@@ -25,7 +25,7 @@ EXPORTS = ("mc_abi_version", "mc_last_error", "mc_launch_count", "mc_reset_launc
            "mc_temporal_attn_bwd", "mc_top1_rows", "mc_motion_loss_fwd", "mc_motion_loss_bwd", "mc_cfg_ddim_step",
            "mc_add_noise", "mc_groupnorm_workspace_bytes", "mc_groupnorm_nhwc", "mc_layernorm", "mc_geglu", "mc_groupnorm_nhwc_stats", "mc_groupnorm_nhwc_bwd", "mc_layernorm_bwd",
            "mc_geglu_bwd", "mc_bias_residual_add", "mc_cross_attn_fwd", "mc_cross_attn_bwd_dq",
-           "mc_self_attn_short_fwd", "mc_spatial_attn_fwd", "mc_spatial_attn_bwd", "mc_spatial_attn_bwd_workspace_bytes")
+           "mc_spatial_attn_fwd", "mc_spatial_attn_bwd", "mc_spatial_attn_bwd_workspace_bytes")
 
 
 def lib() -> ctypes.CDLL:
@@ -80,8 +80,6 @@ def lib() -> ctypes.CDLL:
     L.mc_cross_attn_fwd.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int, c_int] + [c_int64] * 6 + [c_float, P]
     L.mc_cross_attn_bwd_dq.restype = c_int
     L.mc_cross_attn_bwd_dq.argtypes = [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int] + [c_int64] * 8 + [c_float, P]
-    L.mc_self_attn_short_fwd.restype = c_int
-    L.mc_self_attn_short_fwd.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int] + [c_int64] * 4 + [c_float, P]
     L.mc_spatial_attn_fwd.restype = c_int
     L.mc_spatial_attn_fwd.argtypes = [P, P, P, P, P, c_int, c_int, c_int, c_int] + [c_int64] * 8 + [c_float, P]
     L.mc_spatial_attn_bwd_workspace_bytes.restype = c_int64

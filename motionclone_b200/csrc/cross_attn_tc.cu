@@ -385,6 +385,7 @@ static int xattn_check(const char* what, const void* q, const void* k, const voi
 
 #define MC_XATTN_DISPATCH(FN)                       \
   switch (DH) {                                     \
+    case 8: return FN<8>(prm, st);                  \
     case 16: return FN<16>(prm, st);                \
     case 32: return FN<32>(prm, st);                \
     case 40: return FN<40>(prm, st);                \
@@ -408,7 +409,7 @@ extern "C" int mc_cross_attn_fwd(const void* q, const void* k, const void* v, vo
   prm.B = B, prm.Nq = Nq, prm.Nk = Nk, prm.H = H, prm.scale = scale;
   cudaStream_t st = (cudaStream_t)stream;
   MC_XATTN_DISPATCH(launch_xattn)
-  set_error("cross_attn_fwd: unsupported head dim %d (16, 32, 40, 64, 80, 160)", DH);
+  set_error("cross_attn_fwd: unsupported head dim %d (8, 16, 32, 40, 64, 80, 160)", DH);
   return MC_E_UNSUPPORTED;
 }
 
@@ -433,6 +434,6 @@ extern "C" int mc_cross_attn_bwd_dq(const void* q, const void* k, const void* v,
   prm.B = B, prm.Nq = Nq, prm.Nk = Nk, prm.H = H, prm.scale = scale;
   cudaStream_t st = (cudaStream_t)stream;
   MC_XATTN_DISPATCH(launch_xattn_bwd)
-  set_error("cross_attn_bwd_dq: unsupported head dim %d (16, 32, 40, 64, 80, 160)", DH);
+  set_error("cross_attn_bwd_dq: unsupported head dim %d (8, 16, 32, 40, 64, 80, 160)", DH);
   return MC_E_UNSUPPORTED;
 }

@@ -167,6 +167,13 @@ def _device_representation(self, device):
         rep = {k: (v[0].to(device=device, dtype=torch.float16).contiguous(),
                    v[1].to(device=device, dtype=torch.uint8).contiguous())
                for k, v in self.motion_representation_dict.items()}
+        for k, (val, idx) in rep.items():  # a stale / foreign .pt must fail here, as torch.gather would (:91-92)
+            frames = val.shape[-2]
+            if val.shape != idx.shape or val.dim() != 4 or val.shape[-1] != 1:
+                raise ValueError(f"motion representation '{k}': expected value / index tensors of shape [N, heads, L, 1], "
+                                 f"got {tuple(val.shape)} / {tuple(idx.shape)}")
+            if int(idx.max()) >= frames:
+                raise ValueError(f"motion representation '{k}': index {int(idx.max())} >= video_length {frames}")
         self._repr_on_device = (self.motion_representation_dict, device, rep)
         cache = self._repr_on_device
     return cache[2]

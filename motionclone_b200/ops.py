@@ -95,7 +95,7 @@ def temporal_attention_forward(q: Tensor, k: Tensor, v: Optional[Tensor], heads:
         _require(gather_idx, "gather_idx", torch.uint8)
         if gather_idx.numel() != B * P * heads * F or not gather_idx.is_contiguous():
             raise ValueError("gather_idx must be a contiguous uint8 [B*P, H, F, 1] tensor")
-        gathered = torch.empty(rows + (1,), dtype=q.dtype, device=q.device)
+        gathered = torch.zeros(rows + (1,), dtype=q.dtype, device=q.device)
     ev0 = TIMER.start() if TIMER is not None else None
     st = _lib.lib().mc_temporal_attn_fwd(_ptr(q), _ptr(k), _ptr(v if want_o else None), lay,
                                          _ptr(o), _layout_bfpc(o) if want_o else TemporalLayout(0, 0, 0),
@@ -319,8 +319,16 @@ _gn_workspace = {}
 
 
 def glue_kernels_ok(x: Tensor) -> bool:
-    """CUDA fp16 activations take the fused glue kernels (csrc/norm_act.cu); anything else stays on ATen."""
+    """CUDA fp16 activations: the only thing the kernels of this package accept."""
     return x.is_cuda and x.dtype == torch.float16
+
+
+def _require_param(t: Tensor, name: str, like: Tensor, numel: int) -> Tensor:
+    """Norm gains / biases are read as raw fp16 pointers by the kernels: same device, fp16, contiguous, right length."""
+    _require(t, name)
+    if t.device != like.device or t.numel() != numel:
+        raise ValueError(f"{name}: expected {numel} fp16 values on {like.device}, got {t.numel()} on {t.device}")
+    return t.contiguous()
 
 
 def _workspace(x: Tensor, need: int, role: str = "fwd") -> Tensor:
@@ -355,6 +363,7 @@ def groupnorm_nhwc(x: Tensor, weight: Tensor, bias: Tensor, groups: int, eps: fl
         raise ValueError("groupnorm_nhwc expects a 4-D channels_last tensor")
     chan_bias, fpr = _check_chan_bias(x, chan_bias)
     N, C, H, W = x.shape
+    weight, bias = _require_param(weight, "groupnorm weight", x, C), _require_param(bias, "groupnorm bias", x, C)
     y = torch.empty_like(x)  # preserves channels_last
     ws = _workspace(x, int(_lib.lib().mc_groupnorm_workspace_bytes(N, groups)))
     st = _lib.lib().mc_groupnorm_nhwc(_ptr(x), _ptr(chan_bias), fpr, _ptr(y), _ptr(weight), _ptr(bias), _ptr(ws),
@@ -381,9 +390,11 @@ class GroupNormNHWCFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dz):
         x, weight, bias, chan_bias, stats = ctx.saved_tensors
+        _require(dz, "dz")
         dz = dz.contiguous(memory_format=torch.channels_last)
         chan_bias, fpr = _check_chan_bias(x, chan_bias)
         N, C, H, W = x.shape
+        weight, bias = _require_param(weight, "groupnorm weight", x, C), _require_param(bias, "groupnorm bias", x, C)
         dx = torch.empty_like(x)
         ws = _workspace(x, int(_lib.lib().mc_groupnorm_workspace_bytes(N, ctx.groups)), "bwd")
         st = _lib.lib().mc_groupnorm_nhwc_bwd(_ptr(x), _ptr(chan_bias), fpr, _ptr(dz), _ptr(dx), _ptr(stats), _ptr(weight),
@@ -400,6 +411,7 @@ def layernorm(x: Tensor, weight: Tensor, bias: Tensor, eps: float, post_add: Opt
     _require(x, "x")
     x = x.contiguous()
     C = x.shape[-1]
+    weight, bias = _require_param(weight, "layernorm weight", x, C), _require_param(bias, "layernorm bias", x, C)
     y = torch.empty_like(x)
     frames = 0
     if post_add is not None:
@@ -423,8 +435,10 @@ class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
+        _require(dy, "dy")
         dy = dy.contiguous()
         C = x.shape[-1]
+        weight = _require_param(weight, "layernorm weight", x, C)
         dx = torch.empty_like(x)
         st = _lib.lib().mc_layernorm_bwd(_ptr(x), _ptr(dy), _ptr(dx), _ptr(weight), x.numel() // C, C, float(ctx.eps),
                                          _stream())
@@ -550,30 +564,6 @@ class CrossAttentionTC(torch.autograd.Function):
                                       "(frozen projections of a constant prompt embedding)")
         q, k, v = ctx.saved_tensors
         return cross_attention_backward(q, k, v, d_o, ctx.heads, ctx.scale), None, None, None, None
-
-
-SELF_ATTN_SHORT_MAX_TOKENS = 256
-SELF_ATTN_SHORT_HEAD_DIMS = (40, 64, 80, 160)
-
-
-def self_attention_short(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float) -> Tensor:
-    """tcgen05 spatial self-attention for N <= 256 tokens per frame (csrc/self_attn_tc.cu): q, k, v [B, N, C] views
-    with identical strides (column blocks of a fused QKV projection) -> o [B, N, C] contiguous. Inference passes only."""
-    for name, t in (("q", q), ("k", k), ("v", v)):
-        _require(t, name)
-        if t.dim() != 3 or t.stride(2) != 1:
-            raise ValueError(f"{name} must be [B, N, C] with contiguous channels")
-        if t.shape != q.shape or t.stride() != q.stride():
-            raise ValueError("q, k, v must share shape and strides")
-    B, N, C = q.shape
-    o = torch.empty((B, N, C), dtype=q.dtype, device=q.device)
-    ev0 = TIMER.start() if TIMER is not None else None
-    st = _lib.lib().mc_self_attn_short_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), B, N, heads, C // heads, q.stride(0),
-                                           q.stride(1), o.stride(0), o.stride(1), float(scale), _stream())
-    _lib.check(st, "mc_self_attn_short_fwd")
-    if ev0 is not None:  # Q, K, V read + O written
-        TIMER.stop("self_attn_short_fwd", 4 * B * N * C * 2, ev0)
-    return o
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -11,14 +11,13 @@ Design differences (B200-first):
   frame (the reference repeats the text f times, attention.py:100, and re-projects it for every frame);
 * text cross-attention (`attn2`) runs on this package's tcgen05 / TMEM kernels (csrc/cross_attn_tc.cu), forward and
   the gradient w.r.t. the queries (the text K / V carry no gradient on the MotionClone path);
-* spatial SELF-attention at the reference's xformers seam (`_memory_efficient_attention_xformers`, :535-542) is
-  dispatched to `F.scaled_dot_product_attention` (flash kernels, LIBRARY code, same published semantics as
-  xformers.ops.memory_efficient_attention). The hand-written tcgen05 replacement for that seam is the next §8 row;
-  it is not claimed as this package's kernel.
+* spatial SELF-attention at the reference's xformers seam (`_memory_efficient_attention_xformers`, :535-542) runs on this
+  package's tcgen05 + tensor-map TMA flash kernels (csrc/spatial_attn_tc.cu), forward and backward (dQ, dK, dV);
+* there is no ATen / library fallback on this path: CPU tensors, fp32 activations, trainable norm weights or shapes
+  outside the compiled instantiations raise.
 """
 from __future__ import annotations
 
-import os
 from typing import Optional
 
 import torch
@@ -28,14 +27,13 @@ from torch import nn
 from . import ops
 
 
-_XATTN_TC_HEAD_DIMS = (16, 32, 40, 64, 80, 160)  # instantiations of csrc/cross_attn_tc.cu
-# Two measured-and-rejected experiments, kept behind knobs (profiles/README.md):
-# feed-forward row blocking (MB of [rows, 8C] projection per block; 0 = off): +4 ms per DDIM step on B200 — the smaller
-# GEMMs lose more than the L2-resident GEGLU gains. See FeedForward._forward_l2_blocked.
-_FF_CHUNK_BYTES = int(float(os.environ.get("MC_FF_CHUNK_MB", "0")) * (1 << 20))
-# tcgen05 short-sequence self-attention (csrc/self_attn_tc.cu): parity-green, but 70 us against the library's 37 us at
-# N = 256, DH = 160 (generic-load staging of 120 KB per CTA): the library kernel stays the default for `attn1`.
-_SELF_ATTN_TC = os.environ.get("MC_SELF_ATTN_TC", "0") == "1"
+_XATTN_TC_HEAD_DIMS = (8, 16, 32, 40, 64, 80, 160)  # instantiations of csrc/cross_attn_tc.cu
+
+
+def _need_kernels(x, what: str) -> None:
+    if not ops.glue_kernels_ok(x):
+        raise TypeError(f"{what}: expected CUDA fp16 activations, got {x.device} {x.dtype} "
+                        "(motionclone_b200 has no CPU / fp32 / eager path)")
 
 
 def _frozen(*params) -> bool:
@@ -49,16 +47,12 @@ class LayerNorm(nn.LayerNorm):
     def forward(self, x, post_add=None, rows_per_frame: int = 0):
         """post_add [F, C]: added after the norm to the rows of frame (r // rows_per_frame) % F (temporal PE)."""
         c = x.shape[-1]
-        if ops.glue_kernels_ok(x) and self.elementwise_affine and c % 8 == 0 and c <= 1280 \
-                and _frozen(self.weight, self.bias):
-            if torch.is_grad_enabled() and x.requires_grad:
-                return ops.LayerNormFn.apply(x, self.weight, self.bias, self.eps, post_add, rows_per_frame)
-            return ops.layernorm(x, self.weight, self.bias, self.eps, post_add, rows_per_frame)
-        y = super().forward(x)
-        if post_add is not None:
-            f, c = post_add.shape
-            y = (y.view(-1, f, rows_per_frame, c) + post_add.view(1, f, 1, c)).view(y.shape)
-        return y
+        _need_kernels(x, "LayerNorm")
+        if not (self.elementwise_affine and c % 8 == 0 and c <= 1280 and _frozen(self.weight, self.bias)):
+            raise NotImplementedError("LayerNorm kernel: affine, frozen weights, C % 8 == 0, C <= 1280")
+        if torch.is_grad_enabled() and x.requires_grad:
+            return ops.LayerNormFn.apply(x, self.weight, self.bias, self.eps, post_add, rows_per_frame)
+        return ops.layernorm(x, self.weight, self.bias, self.eps, post_add, rows_per_frame)
 
 
 class GroupNormNHWC(nn.GroupNorm):
@@ -68,15 +62,13 @@ class GroupNormNHWC(nn.GroupNorm):
 
     def forward(self, x, silu: bool = False, chan_bias=None):
         """chan_bias [NB, C]: per-(batch row, channel) bias added to x first (the resnet's `+ temb`)."""
-        if x.dim() == 4 and ops.glue_kernels_ok(x) and x.shape[1] % 8 == 0 and x.shape[1] <= 4096 \
-                and x.is_contiguous(memory_format=torch.channels_last) and _frozen(self.weight, self.bias, chan_bias):
-            if torch.is_grad_enabled() and x.requires_grad:
-                return ops.GroupNormNHWCFn.apply(x, self.weight, self.bias, chan_bias, self.num_groups, self.eps, silu)
-            return ops.groupnorm_nhwc(x, self.weight, self.bias, self.num_groups, self.eps, silu, chan_bias)
-        if chan_bias is not None:
-            x = x + chan_bias.repeat_interleave(x.shape[0] // chan_bias.shape[0], dim=0)[:, :, None, None]
-        y = super().forward(x)
-        return F.silu(y) if silu else y
+        _need_kernels(x, "GroupNorm")
+        if not (x.dim() == 4 and x.shape[1] % 8 == 0 and x.shape[1] <= 4096
+                and x.is_contiguous(memory_format=torch.channels_last) and _frozen(self.weight, self.bias, chan_bias)):
+            raise NotImplementedError("GroupNorm kernel: 4-D channels_last input, C % 8 == 0, C <= 4096, frozen weights")
+        if torch.is_grad_enabled() and x.requires_grad:
+            return ops.GroupNormNHWCFn.apply(x, self.weight, self.bias, chan_bias, self.num_groups, self.eps, silu)
+        return ops.groupnorm_nhwc(x, self.weight, self.bias, self.num_groups, self.eps, silu, chan_bias)
 
 
 class GEGLU(nn.Module):
@@ -88,12 +80,12 @@ class GEGLU(nn.Module):
 
     def forward(self, x):
         y = self.proj(x)
-        if ops.glue_kernels_ok(y) and y.shape[-1] % 16 == 0:
-            if torch.is_grad_enabled() and y.requires_grad:
-                return ops.GEGLUFn.apply(y)
-            return ops.geglu(y)  # one pass instead of chunk -> gelu -> mul (csrc/norm_act.cu)
-        h, gate = y.chunk(2, dim=-1)
-        return h * F.gelu(gate)
+        _need_kernels(y, "GEGLU")
+        if y.shape[-1] % 16:
+            raise NotImplementedError("GEGLU kernel: inner dim must be a multiple of 8")
+        if torch.is_grad_enabled() and y.requires_grad:
+            return ops.GEGLUFn.apply(y)
+        return ops.geglu(y)  # one pass instead of chunk -> gelu -> mul (csrc/norm_act.cu)
 
 
 class FeedForward(nn.Module):
@@ -108,30 +100,9 @@ class FeedForward(nn.Module):
         self.net = nn.ModuleList([GEGLU(dim, inner), nn.Dropout(dropout), nn.Linear(inner, dim_out or dim)])
 
     def forward(self, x):
-        if _FF_CHUNK_BYTES > 0 and ops.glue_kernels_ok(x) and not (torch.is_grad_enabled() and x.requires_grad) \
-                and x.is_contiguous():
-            proj, lin = self.net[0].proj, self.net[2]
-            rows = x.numel() // x.shape[-1]
-            rows_per_chunk = max(256, (_FF_CHUNK_BYTES // (2 * proj.out_features)) // 256 * 256)
-            if rows > rows_per_chunk + rows_per_chunk // 2 and proj.out_features % 16 == 0 and lin.bias is not None:
-                return self._forward_l2_blocked(x, rows, rows_per_chunk)
         for m in self.net:
             x = m(x)
         return x
-
-    def _forward_l2_blocked(self, x, rows: int, rows_per_chunk: int):
-        """Inference passes: project -> GEGLU -> project back one row block at a time, sized so the [rows, 8C] projection
-        (the largest intermediate of the UNet: 335 MB at C = 320, 16 frames) is consumed by the GEGLU kernel while it is
-        still in the 126 MB L2, instead of making a round trip through HBM. Same arithmetic, same rounding points."""
-        proj, lin = self.net[0].proj, self.net[2]
-        x2 = x.view(rows, x.shape[-1])
-        out = torch.empty((rows, lin.out_features), dtype=x.dtype, device=x.device)
-        w2t = lin.weight.t()
-        for r0 in range(0, rows, rows_per_chunk):
-            r1 = min(rows, r0 + rows_per_chunk)
-            g = ops.geglu(F.linear(x2[r0:r1], proj.weight, proj.bias))
-            torch.addmm(lin.bias, g, w2t, out=out[r0:r1])
-        return out.view(*x.shape[:-1], lin.out_features)
 
 
 class CrossAttention(nn.Module):
@@ -181,6 +152,21 @@ class CrossAttention(nn.Module):
     def set_processor(self, processor) -> None:
         self.processor = processor
 
+    def invalidate_fused_weights(self) -> None:
+        """Drop the cached [3C, C] / [2C, c] concatenations. Called automatically by load_state_dict and by
+        .to() / .half() / .cuda(); call it by hand after editing to_q / to_k / to_v through `.data` (a LoRA merge as in
+        the reference's convert_lora_safetensor_to_diffusers.py does not bump the tensors' version counters)."""
+        self._fused = None
+        self._fused_kv = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate_fused_weights()
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_fused_weights()
+        return super()._apply(fn, *args, **kwargs)
+
     def fused_qkv_weight(self) -> torch.Tensor:
         """[3C, C] concatenation of to_q/to_k/to_v, rebuilt if any of them was replaced or moved (weights are frozen
         on this path: t2v_video_sample.py:67-68)."""
@@ -199,55 +185,60 @@ class CrossAttention(nn.Module):
         return self._fused_kv[1]
 
     def get_attention_scores(self, query, key, attention_mask=None):
-        """attention.py:564-611: query/key `[B*heads, S, dh]` -> probabilities in the input dtype. For temporal
-        modules (S = frames) this runs on the fused kernel; spatial sizes use the baddbmm/softmax statement."""
+        """attention.py:564-611: query/key `[B*heads, S, dh]` -> probabilities in the input dtype. Only the temporal
+        use (S = frames, motionclone_functions.py:279) exists on this path; it runs on the fused kernel."""
         if attention_mask is not None:
             raise NotImplementedError
         bh, s, dh = query.shape
-        if s in (8, 16, 32) and key.shape[1] == s and query.is_cuda:
-            from . import ops
-            h = self.heads
-            to_bfpc = lambda t: t.reshape(bh // h, h, s, dh).permute(0, 2, 1, 3).reshape(1, bh // h, s, h * dh) \
-                .permute(0, 2, 1, 3)  # noqa: E731  [(B h), S, dh] -> [1, S(frames), B(positions), C]
-            probs = ops.TemporalProbs.apply(to_bfpc(query).contiguous(), to_bfpc(key).contiguous(), h, self.scale)
-            return probs.reshape(bh, s, s)
-        scores = torch.baddbmm(torch.empty(bh, s, key.shape[1], dtype=query.dtype, device=query.device), query,
-                               key.transpose(-1, -2), beta=0, alpha=self.scale)
-        return scores.softmax(dim=-1).to(query.dtype)
+        if s not in (8, 16, 32) or key.shape[1] != s:
+            raise NotImplementedError("get_attention_scores: temporal shapes only (S = key length in {8, 16, 32}); "
+                                      "spatial probabilities are never materialised on this path")
+        h = self.heads
+        to_bfpc = lambda t: t.reshape(bh // h, h, s, dh).permute(0, 2, 1, 3).reshape(1, bh // h, s, h * dh) \
+            .permute(0, 2, 1, 3)  # noqa: E731  [(B h), S, dh] -> [1, S(frames), B(positions), C]
+        probs = ops.TemporalProbs.apply(to_bfpc(query).contiguous(), to_bfpc(key).contiguous(), h, self.scale)
+        return probs.reshape(bh, s, s)
 
     def _memory_efficient_attention_xformers(self, query, key, value, attention_mask=None):
-        """attention.py:535-542 seam: `[B*heads, S, dh]` in, `[B, S, heads*dh]` out."""
+        """attention.py:535-542 seam with the reference's calling convention: `[B*heads, S, dh]` in,
+        `[B, S, heads*dh]` out (the head split is undone into the kernels' `[B, S, C]` views first)."""
+        if attention_mask is not None:
+            raise NotImplementedError
         h = self.heads
         bh, s, dh = query.shape
-        q4, k4, v4 = (t.reshape(bh // h, h, t.shape[1], dh) for t in (query, key, value))
-        o = F.scaled_dot_product_attention(q4, k4, v4, scale=self.scale)
-        return o.permute(0, 2, 1, 3).reshape(bh // h, s, h * dh)
+        merge = lambda t: t.reshape(bh // h, h, t.shape[1], dh).permute(0, 2, 1, 3).reshape(bh // h, t.shape[1], h * dh)  # noqa: E731
+        q, k, v = merge(query), merge(key), merge(value)
+        if key.shape[1] == s:
+            if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+                return ops.SpatialAttentionTC.apply(q, k, v, h, self.scale)
+            return ops.spatial_attention_forward(q, k, v, h, self.scale)[0]
+        if torch.is_grad_enabled() and (k.requires_grad or v.requires_grad):
+            raise NotImplementedError("cross-attention with trainable K / V is not on the MotionClone path")
+        if torch.is_grad_enabled() and q.requires_grad:
+            return ops.CrossAttentionTC.apply(q, k, v, h, self.scale)
+        return ops.cross_attention_forward(q, k, v, h, self.scale)
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, text_batch: Optional[int] = None):
         """hidden_states `[(b f), N, C]`. encoder_hidden_states: `[(b f), n, c]` as in the reference, or `[b, n, c]`
         with `text_batch=b` so the text K/V are projected once per prompt."""
         if attention_mask is not None:
             raise NotImplementedError("no mask reaches attention on the live path (SURVEY appendix)")
+        _need_kernels(hidden_states, "CrossAttention")
         bf, n, c = hidden_states.shape
         h = self.heads
         inner = self.to_q.out_features
         dh = inner // h
         if encoder_hidden_states is None:
-            qkv = F.linear(hidden_states, self.fused_qkv_weight()).view(bf, n, 3, h, dh)
-            q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))  # [(b f), h, N, dh] strided views
+            # spatial self-attention: one fused QKV GEMM, then the tcgen05 + TMA flash kernels on its column blocks
+            qkv = F.linear(hidden_states, self.fused_qkv_weight())  # [(b f), N, 3C]
             if self.processor is not None:
-                self.processor.record_qkv(self, hidden_states, qkv[:, :, 0].reshape(bf, n, inner),
-                                          qkv[:, :, 1].reshape(bf, n, inner), qkv[:, :, 2].reshape(bf, n, inner), None)
-            if _SELF_ATTN_TC and n <= ops.SELF_ATTN_SHORT_MAX_TOKENS and dh in ops.SELF_ATTN_SHORT_HEAD_DIMS \
-                    and ops.glue_kernels_ok(qkv) \
-                    and not (torch.is_grad_enabled() and qkv.requires_grad):
-                # 16x16 / 8x8 latent levels, inference passes: whole key axis in one TMEM tile (csrc/self_attn_tc.cu)
-                qkv3 = qkv.view(bf, n, 3 * inner)
-                o = ops.self_attention_short(qkv3[..., :inner], qkv3[..., inner:2 * inner], qkv3[..., 2 * inner:], h,
-                                             self.scale)
+                self.processor.record_qkv(self, hidden_states, qkv[..., :inner], qkv[..., inner:2 * inner],
+                                          qkv[..., 2 * inner:], None)
+            if torch.is_grad_enabled() and qkv.requires_grad:
+                o = ops.SpatialAttentionFusedTC.apply(qkv, h, self.scale)
             else:
-                o = F.scaled_dot_product_attention(q, k, v, scale=self.scale)  # library flash kernel at the xformers seam
-                o = o.transpose(1, 2).reshape(bf, n, inner)
+                o, _ = ops.spatial_attention_forward(qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:],
+                                                     h, self.scale)
         else:
             ctx = encoder_hidden_states
             b = ctx.shape[0]
@@ -257,17 +248,15 @@ class CrossAttention(nn.Module):
             q = self.to_q(hidden_states).view(b, f * n, inner)                        # frames of one prompt share K/V
             kv = F.linear(ctx, self.fused_kv_weight())                                # [b, 77, 2C]: K | V column blocks
             k, v = kv[..., :inner], kv[..., inner:]
-            if ops.glue_kernels_ok(q) and ctx.shape[1] <= 80 and dh in _XATTN_TC_HEAD_DIMS and not kv.requires_grad:
-                # tcgen05 / TMEM kernels (csrc/cross_attn_tc.cu); dQ only: the text K / V carry no gradient here
-                if torch.is_grad_enabled() and q.requires_grad:
-                    o = ops.CrossAttentionTC.apply(q, k, v, h, self.scale)
-                else:
-                    o = ops.cross_attention_forward(q, k, v, h, self.scale)
-                o = o.view(bf, n, inner)
-            else:  # trainable text branch / long contexts: library kernel at the xformers seam
-                q4, k4, v4 = (t.reshape(b, -1, h, dh).transpose(1, 2) for t in (q, k, v))
-                o = F.scaled_dot_product_attention(q4, k4, v4, scale=self.scale)
-                o = o.transpose(1, 2).reshape(bf, n, inner)
+            if ctx.shape[1] > 80 or dh not in _XATTN_TC_HEAD_DIMS or (torch.is_grad_enabled() and kv.requires_grad):
+                raise NotImplementedError("text cross-attention kernel: <= 80 context tokens, head dim in "
+                                          f"{_XATTN_TC_HEAD_DIMS}, frozen K / V projections of a constant prompt")
+            # tcgen05 / TMEM kernels (csrc/cross_attn_tc.cu); dQ only: the text K / V carry no gradient here
+            if torch.is_grad_enabled() and q.requires_grad:
+                o = ops.CrossAttentionTC.apply(q, k, v, h, self.scale)
+            else:
+                o = ops.cross_attention_forward(q, k, v, h, self.scale)
+            o = o.view(bf, n, inner)
         return self.to_out[1](self.to_out[0](o))
 
 

@@ -110,6 +110,9 @@ class ResnetBlock3D(nn.Module):
         super().__init__()
         if time_embedding_norm != "default" or non_linearity not in ("swish", "silu"):
             raise NotImplementedError("scale_shift / mish are never configured by the reference")
+        if not use_inflated_groupnorm:
+            raise NotImplementedError("use_inflated_groupnorm=False (resnet.py:143-165: GroupNorm statistics pooled across "
+                                      "frames) is not implemented")
         out_channels = in_channels if out_channels is None else out_channels
         self.in_channels, self.out_channels = in_channels, out_channels
         self.time_embedding_norm, self.output_scale_factor = time_embedding_norm, output_scale_factor
@@ -438,6 +441,12 @@ class UNet3DConditionModel(nn.Module):
                 or use_linear_projection or unet_use_cross_frame_attention or unet_use_temporal_attention \
                 or center_input_sample or only_cross_attention not in (False, (False,) * 4, [False] * 4):
             raise NotImplementedError("configuration outside the reference's live path (SURVEY.md appendix A)")
+        if not use_inflated_groupnorm:
+            # resnet.py:143-165 / unet.py:244 use torch.nn.GroupNorm on the 5-D tensor in that mode (statistics pooled
+            # across frames); every shipped config sets use_inflated_groupnorm: true (model_config.yaml:2) and only the
+            # per-frame form is implemented here - refuse instead of silently computing different numbers
+            raise NotImplementedError("use_inflated_groupnorm=False (cross-frame GroupNorm statistics) is not implemented; "
+                                      "all shipped configs use the inflated (per-frame) GroupNorm")
         motion_module_kwargs = dict(motion_module_kwargs or {})
         self.sample_size = sample_size
         self.input_config = None  # set by the driver (t2v_video_sample.py:69)

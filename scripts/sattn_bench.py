@@ -26,7 +26,10 @@ def bench(fn, n=20):
 
 shapes = [("self64", 16, 8, 4096, 40), ("self32", 16, 8, 1024, 80), ("self16", 16, 8, 256, 160), ("self8", 16, 8, 64, 160),
           ("self64_b2", 32, 8, 4096, 40), ("self64_L32", 32, 8, 4096, 40)]
+ONLY = sys.argv[1] if len(sys.argv) > 1 else None   # e.g. `self64`: one shape, few iterations (ncu captures)
 for name, B, H, N, dh in shapes:
+    if ONLY and name != ONLY:
+        continue
     C = H * dh
     qkv = torch.randn(B, N, 3 * C, device=dev, dtype=torch.float16)
     q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]

@@ -63,19 +63,3 @@ for B in (1, 2):
             res["bwd_maxdiff"] = round((dq.float() - dq_lib.float()).abs().max().item(), 5)
             res["bwd_ref_max"] = round(dq_lib.float().abs().max().item(), 5)
         print(json.dumps(res), flush=True)
-
-# ---- short-sequence spatial self-attention (N <= 256 tokens per frame, DH = 160): tcgen05 kernel vs library ----
-for B in (16, 32):
-    for C, N in ((1280, 256), (1280, 64)):
-        dh = C // H
-        scale = dh ** -0.5
-        qkv = torch.randn(B, N, 3 * C, device=dev, dtype=torch.float16)
-        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
-        q4, k4, v4 = (t.reshape(B, N, H, dh).transpose(1, 2) for t in (q, k, v))
-        res = dict(kind="self_short", frames=B, C=C, N=N, MB=round(4 * B * N * C * 2 / 1e6, 1))
-        res["ours_fwd_ms"] = round(timeit(lambda: ops.self_attention_short(q, k, v, H, scale)), 4)
-        res["lib_fwd_ms"] = round(timeit(lambda: F.scaled_dot_product_attention(q4, k4, v4, scale=scale)), 4)
-        o1 = ops.self_attention_short(q, k, v, H, scale)
-        o2 = F.scaled_dot_product_attention(q4, k4, v4, scale=scale).transpose(1, 2).reshape(B, N, C)
-        res["fwd_maxdiff"] = round((o1.float() - o2.float()).abs().max().item(), 5)
-        print(json.dumps(res), flush=True)

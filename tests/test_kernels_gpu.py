@@ -478,27 +478,3 @@ def test_cross_attention_tcgen05_rejects_kv_grad():
     o = ops.CrossAttentionTC.apply(q, k, v, 2, 32 ** -0.5)
     with pytest.raises(NotImplementedError):
         o.float().sum().backward()
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# S1 (short sequences): spatial self-attention with the whole key axis in one TMEM tile
-# ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,N,H,DH", [(4, 256, 8, 160), (3, 64, 8, 160), (2, 200, 8, 80), (2, 256, 8, 40), (1, 129, 2, 64),
-                                      (32, 256, 8, 160), (1, 16, 8, 160)])
-def test_self_attention_short_tcgen05(B, N, H, DH):
-    """reference: CrossAttention attn1 through xformers.ops.memory_efficient_attention (models/attention.py:535-542):
-    softmax(q k^T * dh^-0.5) v with fp32 softmax statistics; q, k, v are column blocks of one fused projection."""
-    ops, dev = _ops(), _dev()
-    C = H * DH
-    g = torch.Generator().manual_seed(N + DH)
-    qkv = torch.randn(B, N, 3 * C, generator=g).to(dev, torch.float16)
-    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
-    scale = DH ** -0.5
-    o = ops.self_attention_short(q, k, v, H, scale)
-    qh, kh, vh = (t.float().reshape(B, N, H, DH).transpose(1, 2) for t in (q, k, v))
-    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1) @ vh).transpose(1, 2).reshape(B, N, C)
-    lib = torch.nn.functional.scaled_dot_product_attention(
-        *(t.reshape(B, N, H, DH).transpose(1, 2) for t in (q, k, v)), scale=scale).transpose(1, 2).reshape(B, N, C)
-    err, err_lib = (o.float() - ref).abs().max().item(), (lib.float() - ref).abs().max().item()
-    assert torch.isfinite(o).all()
-    assert err <= max(3e-3, 2.0 * err_lib), (err, err_lib)
