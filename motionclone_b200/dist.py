@@ -54,21 +54,30 @@ def unpack_representation(buf: torch.Tensor, manifest: list) -> Dict[str, List[t
     return out
 
 
-def broadcast_representation(rep, device, src: int = 0):
-    """B1: rank `src` passes its representation, the others pass None; everyone gets the dict."""
+def representation_manifest(module_names: Sequence[str], positions: int, heads: int, frames: int) -> list:
+    """The layout of the packed motion representation is a pure function of the configuration: for every guided module
+    (utils/motionclone_functions.py:264-266) top-1 values fp16 and indices uint8 of shape [positions, heads, frames, 1]
+    (:79-81), positions = (h/32) * (w/32) for `up_blocks.1`. Every rank derives it locally, so the broadcast below is the
+    ONLY collective of the path."""
+    shape = (int(positions), int(heads), int(frames), 1)
+    return [(str(n), shape, shape) for n in module_names]
+
+
+def manifest_nbytes(manifest: list) -> int:
+    return sum(2 * int(torch.Size(v).numel()) + int(torch.Size(i).numel()) for _, v, i in manifest)
+
+
+def broadcast_representation(rep, device, manifest: list, src: int = 0):
+    """B1: rank `src` passes its representation, the others pass None; everyone gets the dict.
+    Exactly one collective: a `broadcast` of the packed byte buffer whose layout `manifest` every rank already knows."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return rep
-    rank = dist.get_rank()
-    meta = [None]
-    buf = None
-    if rank == src:
-        buf, manifest = pack_representation(rep)
-        meta = [(manifest, buf.numel())]
-    dist.broadcast_object_list(meta, src=src)  # shapes only (host side, a few hundred bytes)
-    manifest, nbytes = meta[0]
-    if rank != src:
-        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
-    else:
+    if dist.get_rank() == src:
+        buf, have = pack_representation(rep)
+        if [tuple(m) for m in have] != [tuple(m) for m in manifest]:
+            raise ValueError("motion representation does not match the manifest derived from the configuration")
         buf = buf.to(device)
-    dist.broadcast(buf, src=src)  # the one data collective
+    else:
+        buf = torch.empty(manifest_nbytes(manifest), dtype=torch.uint8, device=device)
+    dist.broadcast(buf, src=src)
     return unpack_representation(buf, manifest)

@@ -263,12 +263,27 @@ def _feed_forward(sd: _SD, x: Tensor) -> Tensor:
     return sd.linear("net.2", h * F.gelu(gate))
 
 
+# models/attention.py:449-459: with xformers enabled (the reference's GPU configuration, pipelines' enable_xformers...)
+# spatial attention goes through xformers.ops.memory_efficient_attention (:535-542); without it through the math path
+# (:461-490). "math" is the parity truth (CPU, and fp16 on a GPU); "sdpa" = the library flash kernel standing in for the
+# absent xformers wheel, used ONLY by bench.py's same-GPU comparator leg (`gpu_reference`), never by a parity test.
+SPATIAL_ATTENTION = "math"
+
+
+def attention_xformers_seam(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float) -> Tensor:
+    """models/attention.py:535-542 with torch's fused SDPA in the role of xformers.ops.memory_efficient_attention."""
+    b, s, c = q.shape
+    q4, k4, v4 = (t.reshape(b, t.shape[1], heads, c // heads).transpose(1, 2) for t in (q, k, v))
+    return F.scaled_dot_product_attention(q4, k4, v4, scale=scale).transpose(1, 2).reshape(b, s, c)
+
+
 def _cross_attention(sd: _SD, x: Tensor, ctx: Optional[Tensor], heads: int) -> Tensor:
-    """models/attention.py:387-459 via the math path (:461-490)."""
+    """models/attention.py:387-459 via the math path (:461-490) [or the xformers seam, see SPATIAL_ATTENTION]."""
     ctx = x if ctx is None else ctx
     q, k, v = sd.linear("to_q", x), sd.linear("to_k", ctx), sd.linear("to_v", ctx)
     scale = (q.shape[-1] // heads) ** -0.5
-    return sd.linear("to_out.0", attention_math(q, k, v, heads, scale))
+    core = attention_xformers_seam if SPATIAL_ATTENTION == "sdpa" else attention_math
+    return sd.linear("to_out.0", core(q, k, v, heads, scale))
 
 
 def _spatial_transformer(sd: _SD, x: Tensor, text: Tensor, heads: int, groups: int) -> Tensor:

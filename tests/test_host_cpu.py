@@ -104,7 +104,9 @@ g = torch.Generator().manual_seed(0)
 rep = None
 if rank == 0:
     rep = {f"m{i}": [torch.rand(4, 8, 16, 1, generator=g).half(), torch.randint(0, 16, (4, 8, 16, 1), generator=g).to(torch.uint8)] for i in range(6)}
-got = mcdist.broadcast_representation(rep, torch.device("cpu"))
+manifest = mcdist.representation_manifest([f"m{i}" for i in range(6)], 4, 8, 16)
+assert mcdist.manifest_nbytes(manifest) == 6 * 4 * 8 * 16 * 3
+got = mcdist.broadcast_representation(rep, torch.device("cpu"), manifest)
 g2 = torch.Generator().manual_seed(0)
 for i in range(6):
     v = torch.rand(4, 8, 16, 1, generator=g2).half(); ix = torch.randint(0, 16, (4, 8, 16, 1), generator=g2).to(torch.uint8)

@@ -109,7 +109,7 @@ def test_motion_representation_vs_reference(run):
     g = run["g"]
     names = list(run["rep"].keys())
     assert names == [str(n) for n in g["repr_names"]]
-    total, mismatch = 0, 0
+    total, mismatch, worst_gaps = 0, 0, []
     for i, n in enumerate(names):
         val, idx = run["rep"][n]
         ref_val, ref_idx = torch.from_numpy(g[f"repr_val_{i}"]), torch.from_numpy(g[f"repr_idx_{i}"])
@@ -119,12 +119,16 @@ def test_motion_representation_vs_reference(run):
         mismatch += int(bad.sum())
         # values: fp16 probabilities vs fp32 ones, 1e-2 absolute (inputs to the softmax carry fp16 error of the UNet)
         assert (val.float().cpu() - ref_val).abs().max().item() < 2.5e-2
-        if i == 0 and "extract_probs_0" in g:  # every index mismatch must be a near-tie in the REFERENCE's own probabilities
-            p = torch.from_numpy(g["extract_probs_0"])
-            top2 = p.topk(2, dim=-1).values
-            gap = (top2[..., 0] - top2[..., 1]).unsqueeze(-1)
-            assert (gap[bad] < 5e-2).all(), "top-1 index differs where the reference's top-2 gap is not a near-tie"
-    print(run["case"], f"top-1 index mismatches vs fp32 reference: {mismatch}/{total}")
+        # every index mismatch, in EVERY guided module, must sit on a row that is a near-tie in the REFERENCE's own fp32
+        # probabilities (fixture key extract_top2gap_i = top-1 minus top-2 probability of the reference's rows). The
+        # bound is an fp16 statement: q, k reach the softmax through ~100 fp16 layers, so two probabilities closer than
+        # the accumulated fp16 error of a score (a few 1e-2 relative) can legitimately swap order.
+        gap = torch.from_numpy(g[f"extract_top2gap_{i}"]).unsqueeze(-1)
+        worst = float(gap[bad].max()) if bool(bad.any()) else 0.0
+        worst_gaps.append(worst)
+        assert worst < 5e-2, f"module {i}: top-1 index differs where the reference's top-2 gap is {worst:.3e}"
+    print(run["case"], f"top-1 index mismatches vs fp32 reference: {mismatch}/{total}; largest reference top-2 gap on a "
+          f"mismatching row, per module: {[f'{w:.2e}' for w in worst_gaps]}")
     assert mismatch / total < 0.02
 
 
