@@ -7,7 +7,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint8, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmotionclone_b200.so")
+# MC_LIB: path of an alternative build of the same library (tile-shape experiments in scripts/; same ABI, same symbols)
+LIB_PATH = os.environ.get("MC_LIB") or os.path.join(_HERE, "libmotionclone_b200.so")
 
 
 class TemporalLayout(Structure):

@@ -614,7 +614,7 @@ def spatial_attention_backward(q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: 
     _require(lse, "lse", torch.float32)
     B, N, C = q.shape
     dqkv = torch.empty((B, N, 3 * C), dtype=q.dtype, device=q.device)
-    ws = torch.empty((B, heads, N), dtype=torch.float32, device=q.device)
+    ws = torch.empty(int(_lib.lib().mc_spatial_attn_bwd_workspace_bytes(B, N, heads)), dtype=torch.uint8, device=q.device)
     ev0 = TIMER.start() if TIMER is not None else None
     st = _lib.lib().mc_spatial_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(d_o), _ptr(lse),
                                         ctypes.c_void_p(dqkv.data_ptr()), ctypes.c_void_p(dqkv.data_ptr() + 2 * C),

@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import motionclone_b200 as mc
 from motionclone_b200.synthetic import UNET_SD15_CONFIG, synthetic_inputs
-from bench import INFER
+from bench import CONFIGS
+INFER = {k: v for k, v in CONFIGS["object"].items() if k not in ("workload", "distinct_prompts")}
 
 dev = torch.device("cuda:0")
 infer = dict(INFER)

@@ -122,11 +122,12 @@ def test_motion_representation_vs_reference(run):
         # every index mismatch, in EVERY guided module, must sit on a row that is a near-tie in the REFERENCE's own fp32
         # probabilities (fixture key extract_top2gap_i = top-1 minus top-2 probability of the reference's rows). The
         # bound is an fp16 statement: q, k reach the softmax through ~100 fp16 layers, so two probabilities closer than
-        # the accumulated fp16 error of a score (a few 1e-2 relative) can legitimately swap order.
+        # the accumulated fp16 error of a score can legitimately swap order (measured on B200: every mismatching row has a
+        # reference gap <= 3.7e-3, i.e. <= 30 fp16 ulps of a probability ~ 1/L; the bar is 8e-3).
         gap = torch.from_numpy(g[f"extract_top2gap_{i}"]).unsqueeze(-1)
         worst = float(gap[bad].max()) if bool(bad.any()) else 0.0
         worst_gaps.append(worst)
-        assert worst < 5e-2, f"module {i}: top-1 index differs where the reference's top-2 gap is {worst:.3e}"
+        assert worst < 8e-3, f"module {i}: top-1 index differs where the reference's top-2 gap is {worst:.3e}"
     print(run["case"], f"top-1 index mismatches vs fp32 reference: {mismatch}/{total}; largest reference top-2 gap on a "
           f"mismatching row, per module: {[f'{w:.2e}' for w in worst_gaps]}")
     assert mismatch / total < 0.02

@@ -117,6 +117,9 @@ def test_single_step_vs_device_oracle(bench_case, kind):
     pipe._repr_on_device = None
     pipe.scheduler.customized_set_timesteps(icfg["inference_steps"], icfg["guidance_steps"], icfg["guidance_scale"],
                                             device=c["dev"], timestep_spacing_type="uneven")
+    # the per-sample state sample_video sets up before its loop (guidance.py: text embeddings, loss weight, SparseCtrl)
+    pipe.text_embeddings = h(inp["text_embeddings"])
+    pipe.motion_scale = icfg["motion_guidance_weight"]
     pipe.add_controlnet = c["cn"] is not None
     if c["cn"] is not None:  # what sample_video does at guidance.py:224-230
         pipe.controlnet_images = c["cn"]["images"]
