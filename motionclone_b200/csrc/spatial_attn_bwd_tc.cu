@@ -475,7 +475,6 @@ static int launch_spatial_bwd(const void* q, const void* k, const void* v, const
            make_maps_rows<DH>(q64, q, H, N, B, q_sr, q_sb, kBT) | make_maps_rows<DH>(do64, d_o, H, N, B, do_sr, do_sb, kBT) |
            make_maps_rows<DH>(k64, k, H, N, B, k_sr, k_sb, kBT) | make_maps_rows<DH>(v64, v, H, N, B, v_sr, v_sb, kBT);
   if (rc) {
-    set_error("spatial_attn_bwd: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned, strides multiples of 8)");
     return MC_E_CUDA;
   }
   float* lse2 = workspace;

@@ -7,17 +7,20 @@
 // statistics, one rounding of the output (xformers / flash semantics - SURVEY.md appendix "Attention numerics").
 //
 // Forward, one CTA = one (frame, head, 128-query tile); 160 threads = 4 softmax warps (thread r owns query row r = TMEM
-// lane r) + 1 producer warp whose lane 0 issues every TMA load and every MMA. Two CTAs share an SM (TMEM 2 x 256 columns),
-// so one CTA's exponentials overlap the other's MMAs. Per 128-key tile j:
-//   producer:  S = Q K_j^T           tcgen05.mma M=128 N=128 K=DH -> TMEM columns [0,128)          -> commit s_full
-//   softmax :  S -> registers (128 fp32 per thread), release S (s_free: the producer may issue S_{j+1} at once),
-//              row max / exp2 / row sum, P -> fp16 -> shared memory (K-major SW128)                -> arrive p_full
-//   producer:  O += P V_j            tcgen05.mma M=128 N=DH K=128 (V MN-major: no transpose)       -> commit pv_done
-// O stays in TMEM for the whole key loop. The running maximum is only raised when a row's maximum grows by more than
-// 2^8 (P <= 256 fits fp16; exactness is unaffected because the row sum uses the same reference maximum); only then does
-// the softmax warp rescale its 32 rows of O in TMEM (tcgen05.ld -> multiply -> tcgen05.st) before releasing P.
+// lane r) + 1 producer warp whose lane 0 issues every TMA load and every MMA. Per BN-key tile j (BN = 64 for head dims
+// <= 48, where four CTAs then share an SM - 16 softmax warps - and 128 otherwise, two CTAs per SM):
+//   producer:  S = Q K_j^T           tcgen05.mma M=128 N=BN K=DH -> TMEM columns [0,BN)            -> commit s_full
+//   softmax :  S -> registers (BN fp32 per thread), release S (s_free: the producer may issue S_{j+1} at once),
+//              row max / exp2, P -> fp16 -> shared memory (K-major SW128)                          -> arrive p_full
+//   producer:  O += P V_j, L += P 1  tcgen05.mma M=128 N=DH (+16) K=BN (V MN-major: no transpose)  -> commit pv_done
+// The kernel is bound by the exponentials (16 / cycle / SM against a 128 x 128 x 48 MMA pair of ~400 cycles), so every
+// instruction taken out of the softmax warps counts: the row sum is NOT accumulated by the threads but by the tensor core,
+// as 16 extra accumulator columns L = P x (a tile of ones) next to O, from the same fp16 P the numerator uses.
+// O and L stay in TMEM for the whole key loop. The running maximum is only raised when a row's maximum grows by more than
+// 2^8 (P <= 256 fits fp16; exactness is unaffected because numerator and denominator share the reference maximum); only
+// then does the softmax warp rescale its 32 rows of O | L in TMEM (tcgen05.ld -> multiply -> tcgen05.st) before releasing P.
 // K and V are single-buffered: K_{j+1} is requested the moment S_j has completed and V_{j+1} when P V_j has - both land
-// long before the exp-bound softmax of tile j (>= 1024 cycles: 16 384 exponentials at 16 / cycle / SM) is through.
+// before the exp-bound softmax of tile j is through; the CTAs sharing the SM cover each other's remaining bubbles.
 #include <math.h>
 
 #include "tma_common.cuh"
@@ -25,11 +28,6 @@
 namespace mc {
 
 constexpr int kFM = 128;         // query rows per CTA (UMMA M)
-#ifndef MC_SA_BN
-#define MC_SA_BN 128
-#endif
-constexpr int kFN = MC_SA_BN;    // keys per tile (UMMA N of S, K extent of P V): 128 or 64
-static_assert(kFN == 128 || kFN == 64, "key tile");
 constexpr int kFThreads = 160;   // 4 softmax warps + 1 producer warp
 constexpr float kRescaleThreshold = 8.f;  // log2 units
 
@@ -44,27 +42,28 @@ struct FAParams {
 template <int DH>
 struct FACfg {
   using T = TileParts<DH>;            // Q tile (128 rows)
-  using TK = TileParts<DH, kFN>;      // K / V tiles
   static constexpr int DHP = T::DHP;
-  static constexpr int P_BYTES = (kFN / 64) * 16384;        // P [128 q][kFN keys] fp16: K-major SW128 parts of 64 keys
+  static constexpr int BN = DHP <= 48 ? 64 : 128;   // keys per tile (UMMA N of S, K extent of P V)
+  using TK = TileParts<DH, BN>;       // K / V tiles
+  static constexpr int P_BYTES = (BN / 64) * 16384;         // P [128 q][BN keys] fp16: K-major SW128 parts of 64 keys
+  static constexpr int ONES_BYTES = BN * 32;                 // [BN keys][16] fp16 ones (MN-major SW32 part; all 1.0)
   static constexpr int OFF_Q = 0, OFF_K = T::BYTES, OFF_V = OFF_K + TK::BYTES, OFF_P = OFF_V + TK::BYTES;
-  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int OFF_ONES = OFF_P + P_BYTES, OFF_BAR = OFF_ONES + ONES_BYTES;
   static constexpr int SMEM = OFF_BAR + 128 + 1024;          // + alignment slack (dynamic smem base is 16 B aligned)
-  static constexpr int O_COL = kFN;                          // O at TMEM columns [kFN, kFN + DHP)
-  static constexpr int TCOLS = (kFN + DHP <= 128) ? 128 : ((kFN + DHP <= 256) ? 256 : 512);
-#ifdef MC_SA_CTAS
-  static constexpr int CTAS_PER_SM = (MC_SA_CTAS * TCOLS <= 512 && MC_SA_CTAS * SMEM <= 227 * 1024) ? MC_SA_CTAS : 1;
-#else
-  static constexpr int CTAS_PER_SM = (2 * TCOLS <= 512 && 2 * SMEM <= 227 * 1024) ? 2 : 1;
-#endif
+  static constexpr int O_COL = BN;                           // O at TMEM columns [BN, BN + DHP), L at [BN + DHP, + 16)
+  static constexpr int L_COL = BN + DHP;
+  static constexpr int ACC_COLS = DHP + 16;                  // O | L
+  static constexpr int TCOLS = (BN + ACC_COLS <= 128) ? 128 : ((BN + ACC_COLS <= 256) ? 256 : 512);
+  static constexpr int CTAS_TMEM = 512 / TCOLS, CTAS_SMEM = (227 * 1024) / SMEM;
+  static constexpr int CTAS_PER_SM = CTAS_TMEM < CTAS_SMEM ? CTAS_TMEM : (CTAS_SMEM < 1 ? 1 : CTAS_SMEM);
 };
 
-// S tile: A = Q (K-major, 128 rows), B = K (K-major, kFN rows); one MMA per k16 step over the head dim
+// S tile: A = Q (K-major, 128 rows), B = K (K-major, BN rows); one MMA per k16 step over the head dim
 template <int DH>
 __device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint32_t sA, uint32_t sB) {
   using T = TileParts<DH>;
-  using TK = TileParts<DH, kFN>;
-  const uint32_t idesc = umma_idesc_f16(kFM, kFN, false, false);
+  using TK = typename FACfg<DH>::TK;
+  const uint32_t idesc = umma_idesc_f16(kFM, FACfg<DH>::BN, false, false);
   uint32_t acc = 0;
 #pragma unroll
   for (int p = 0; p < T::N64; ++p)
@@ -80,22 +79,24 @@ __device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint32_t sA, uint32_t 
   }
 }
 
-// D[128 x DH] (+)= A[128 x kFN] B[kFN x DH]: A = K-major SW128 parts (64 keys each) written by threads (P), B = the V tile
-// read MN-major (its rows are the K dimension). One MMA per (k16 step, part of B).
+// O[128 x DH] (+)= P[128 x BN] V[BN x DH] and L[128 x 16] (+)= P 1: A = K-major SW128 parts (64 keys each) written by
+// threads, B = the V tile read MN-major (its rows are the K dimension) / the tile of ones. One MMA per (k16 step, part).
 template <int DH>
-__device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t sA, uint32_t sB, bool accumulate) {
-  using T = TileParts<DH, kFN>;
+__device__ __forceinline__ void issue_pv(uint32_t o_tmem, uint32_t sA, uint32_t sB, uint32_t sOnes, bool accumulate) {
+  using X = FACfg<DH>;
+  using T = typename X::TK;
   const uint32_t idesc64 = umma_idesc_f16(kFM, T::W64, false, true);
   const uint32_t idesc16 = umma_idesc_f16(kFM, 16, false, true);
 #pragma unroll
-  for (int ks = 0; ks < kFN / 16; ++ks) {
+  for (int ks = 0; ks < X::BN / 16; ++ks) {
     const uint64_t a = desc_k128(sA + (ks >> 2) * 16384, ks & 3);
     const uint32_t acc = (accumulate || ks > 0) ? 1u : 0u;
 #pragma unroll
-    for (int p = 0; p < T::N64; ++p) umma_f16(d_tmem + p * 64, a, desc_mn128(sB + T::part64_off(p), ks), idesc64, acc);
+    for (int p = 0; p < T::N64; ++p) umma_f16(o_tmem + p * 64, a, desc_mn128(sB + T::part64_off(p), ks), idesc64, acc);
 #pragma unroll
     for (int p = 0; p < T::N16; ++p)
-      umma_f16(d_tmem + T::N64 * 64 + p * 16, a, desc_mn32(sB + T::part16_off(p), ks), idesc16, acc);
+      umma_f16(o_tmem + T::N64 * 64 + p * 16, a, desc_mn32(sB + T::part16_off(p), ks), idesc16, acc);
+    umma_f16(o_tmem + X::DHP, a, desc_mn32(sOnes, ks), idesc16, acc);
   }
 }
 
@@ -108,7 +109,7 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
   using X = FACfg<DH>;
   using T = TileParts<DH>;
   using TK = typename X::TK;
-  constexpr int DHP = X::DHP;
+  constexpr int DHP = X::DHP, BN = X::BN;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -116,6 +117,7 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
   uint8_t* sK = smem + X::OFF_K;
   uint8_t* sV = smem + X::OFF_V;
   uint8_t* sP = smem + X::OFF_P;
+  uint8_t* sOnes = smem + X::OFF_ONES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X::OFF_BAR);
   uint64_t* bar_q = bars + 0;      // Q landed                       (tx)
   uint64_t* bar_k = bars + 1;      // K_j landed                     (tx, phase j & 1)
@@ -129,7 +131,7 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * kFM, N = prm.N;
-  const int T_tiles = (N + kFN - 1) / kFN;
+  const int T_tiles = (N + BN - 1) / BN;
 
   if (warp == 4) {
     tmem_alloc<X::TCOLS>(tmem_slot);
@@ -139,6 +141,10 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
       fence_mbar_init();
       tma_prefetch_desc(&mq128), tma_prefetch_desc(&mk128), tma_prefetch_desc(&mv128);
     }
+  } else {
+    for (int i = tid; i < X::ONES_BYTES / 16; i += 128)  // fp16 1.0 everywhere: any swizzle of it is itself
+      reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -151,9 +157,9 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
       mbar_arrive_expect_tx(bar_q, T::BYTES);
       tma_load_tile<DH>(sQ, &mq128, &mq32, bar_q, q0, h, b);
       mbar_arrive_expect_tx(bar_k, TK::BYTES);
-      tma_load_tile<DH, kFN>(sK, &mk128, &mk32, bar_k, 0, h, b);
+      tma_load_tile<DH, BN>(sK, &mk128, &mk32, bar_k, 0, h, b);
       mbar_arrive_expect_tx(bar_v, TK::BYTES);
-      tma_load_tile<DH, kFN>(sV, &mv128, &mv32, bar_v, 0, h, b);
+      tma_load_tile<DH, BN>(sV, &mv128, &mv32, bar_v, 0, h, b);
       mbar_wait(bar_q, 0);
       mbar_wait(bar_k, 0);
       tc_fence_after();
@@ -164,7 +170,7 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
         mbar_wait(s_full, ph);  // S_j completed: the K buffer is free
         if (j + 1 < T_tiles) {
           mbar_arrive_expect_tx(bar_k, TK::BYTES);
-          tma_load_tile<DH, kFN>(sK, &mk128, &mk32, bar_k, (j + 1) * kFN, h, b);
+          tma_load_tile<DH, BN>(sK, &mk128, &mk32, bar_k, (j + 1) * BN, h, b);
           mbar_wait(bar_k, ph ^ 1);
           mbar_wait(s_free, ph);  // every softmax thread holds S_j in registers
           tc_fence_after();
@@ -174,12 +180,12 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
         mbar_wait(bar_v, ph);
         mbar_wait(p_full, ph);
         tc_fence_after();
-        issue_pv<DH>(tmem_base + X::O_COL, smem_u32(sP), smem_u32(sV), j > 0);
+        issue_pv<DH>(tmem_base + X::O_COL, smem_u32(sP), smem_u32(sV), smem_u32(sOnes), j > 0);
         umma_commit(pv_done);
         if (j + 1 < T_tiles) {
           mbar_wait(pv_done, ph);  // V buffer (and P buffer) free
           mbar_arrive_expect_tx(bar_v, TK::BYTES);
-          tma_load_tile<DH, kFN>(sV, &mv128, &mv32, bar_v, (j + 1) * kFN, h, b);
+          tma_load_tile<DH, BN>(sV, &mv128, &mv32, bar_v, (j + 1) * BN, h, b);
         }
       }
     }
@@ -187,29 +193,29 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
     // ================= softmax warps: thread = query row =================
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const float c = prm.scale_log2e;
-    float m_used = -INFINITY, l = 0.f;
+    float m_used = -INFINITY;
     for (int j = 0; j < T_tiles; ++j) {
       const uint32_t ph = j & 1;
       mbar_wait(s_full, ph);
       tc_fence_after();
-      uint32_t s[kFN];
+      uint32_t s[BN];
 #pragma unroll
-      for (int cc = 0; cc < kFN / 32; ++cc) tmem_ld32(lane_addr + cc * 32, s + cc * 32);
+      for (int cc = 0; cc < BN / 32; ++cc) tmem_ld32(lane_addr + cc * 32, s + cc * 32);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
 
-      const int kvalid = N - j * kFN;  // keys of this tile that exist (>= 1)
-      if (kvalid < kFN) {
+      const int kvalid = N - j * BN;  // keys of this tile that exist (>= 1)
+      if (kvalid < BN) {
 #pragma unroll
-        for (int i = 0; i < kFN; ++i)
+        for (int i = 0; i < BN; ++i)
           if (i >= kvalid) s[i] = 0xff800000u;  // -inf
       }
       float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
             mx3 = __uint_as_float(s[3]);
 #pragma unroll
-      for (int i = 4; i < kFN; i += 4) {
+      for (int i = 4; i < BN; i += 4) {
         mx0 = fmaxf(mx0, __uint_as_float(s[i])), mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(s[i + 2])), mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
       }
@@ -222,13 +228,12 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
         if (__any_sync(0xffffffffu, grow)) {
           const float m_new = grow ? mxc : m_used;
           const float alpha = ex2_approx(m_used - m_new);
-          l *= alpha;
           m_used = m_new;
-          mbar_wait(pv_done, ph ^ 1);  // O holds tiles 0..j-1
+          mbar_wait(pv_done, ph ^ 1);  // O | L hold tiles 0..j-1
           waited_pv = true;
           tc_fence_after();
 #pragma unroll
-          for (int cc = 0; cc < DHP / 16; ++cc) {
+          for (int cc = 0; cc < X::ACC_COLS / 16; ++cc) {
             uint32_t r[16];
             tmem_ld16(lane_addr + X::O_COL + cc * 16, r);
             tmem_ld_wait();
@@ -240,20 +245,17 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
           tc_fence_before();
         }
       }
-      // p = exp2(s*c - m_used); packed to fp16 pairs in place (s[0..63] hold the 128 probabilities)
+      // p = exp2(s*c - m_used), packed to fp16 pairs in place (s[0 .. BN/2) then hold the BN probabilities)
       const float negm = -m_used;
-      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < kFN; i += 2) {
+      for (int i = 0; i < BN; i += 2) {
         const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), c, negm));
         const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), c, negm));
-        l0 += p0, l1 += p1;
         s[i >> 1] = pack_half2(p0, p1);
       }
-      l += l0 + l1;
       if (j > 0 && !waited_pv) mbar_wait(pv_done, ph ^ 1);  // P_{j-1} consumed: the P buffer is free
 #pragma unroll
-      for (int ch = 0; ch < kFN / 8; ++ch) {  // 16-byte chunk ch = keys [8 ch, 8 ch + 8)
+      for (int ch = 0; ch < BN / 8; ++ch) {  // 16-byte chunk ch = keys [8 ch, 8 ch + 8)
         uint8_t* dst = sP + (ch >> 3) * 16384 + sw128_chunk_off(tid, ch & 7);
         *reinterpret_cast<uint4*>(dst) = make_uint4(s[4 * ch], s[4 * ch + 1], s[4 * ch + 2], s[4 * ch + 3]);
       }
@@ -265,6 +267,13 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
     mbar_wait(pv_done, (T_tiles - 1) & 1);
     tc_fence_after();
     const int row = q0 + tid;
+    float l;
+    {
+      uint32_t r[16];
+      tmem_ld16(lane_addr + X::L_COL, r);
+      tmem_ld_wait();
+      l = __uint_as_float(r[0]);
+    }
     const float inv = 1.f / l;
     __half* orow = prm.o + (int64_t)b * prm.o_sb + (int64_t)row * prm.o_sr + h * DH;
 #pragma unroll
@@ -291,7 +300,10 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<X::TCOLS>(tmem_base);
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc<X::TCOLS>(tmem_base);
+  }
 }
 
 struct AttnMaps {
@@ -314,9 +326,8 @@ static int launch_spatial_fwd(const void* q, const void* k, const void* v, const
                               int64_t k_sb, int64_t k_sr, int64_t v_sb, int64_t v_sr, cudaStream_t st) {
   using X = FACfg<DH>;
   AttnMaps mq, mk, mv;
-  if (make_maps<DH>(mq, q, prm.H, prm.N, prm.B, q_sr, q_sb, kFM) || make_maps<DH>(mk, k, prm.H, prm.N, prm.B, k_sr, k_sb, kFN) ||
-      make_maps<DH>(mv, v, prm.H, prm.N, prm.B, v_sr, v_sb, kFN)) {
-    set_error("spatial_attn_fwd: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned, strides multiples of 8)");
+  if (make_maps<DH>(mq, q, prm.H, prm.N, prm.B, q_sr, q_sb, kFM) || make_maps<DH>(mk, k, prm.H, prm.N, prm.B, k_sr, k_sb, X::BN) ||
+      make_maps<DH>(mv, v, prm.H, prm.N, prm.B, v_sr, v_sb, X::BN)) {
     return MC_E_CUDA;
   }
   auto kern = spatial_attn_fwd_kernel<DH>;

@@ -39,7 +39,10 @@ inline mc_encode_tiled_fn tensor_map_encoder() {
 inline int make_attn_tensor_map(CUtensorMap* map, const void* base, int DH, int H, int64_t rows, int64_t frames,
                                 int64_t stride_r, int64_t stride_b, int box_e, int box_rows, bool swizzle128) {
   mc_encode_tiled_fn enc = tensor_map_encoder();
-  if (!enc) return -1;
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled: driver entry point unavailable (cudaGetDriverEntryPoint failed)");
+    return -1;
+  }
   cuuint64_t gdim[4] = {(cuuint64_t)DH, (cuuint64_t)H, (cuuint64_t)rows, (cuuint64_t)frames};
   cuuint64_t gstr[3] = {(cuuint64_t)DH * 2, (cuuint64_t)stride_r * 2, (cuuint64_t)stride_b * 2};
   if (frames == 1) gstr[2] = gstr[1] * (cuuint64_t)rows;  // unused dimension: any legal stride
@@ -48,6 +51,10 @@ inline int make_attn_tensor_map(CUtensorMap* map, const void* base, int DH, int 
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    set_error("cuTensorMapEncodeTiled -> CUresult %d: base %p dims (%d, %d, %lld, %lld) strides (%lld, %lld) elements, box "
+              "(%d, 1, %d, 1), swizzle %s", (int)r, base, DH, H, (long long)rows, (long long)frames, (long long)stride_r,
+              (long long)stride_b, box_e, box_rows, swizzle128 ? "128B" : "32B");
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
