@@ -8,19 +8,21 @@
 //
 // Forward, one CTA = one (frame, head, 128-query tile); 160 threads = 4 softmax warps (thread r owns query row r = TMEM
 // lane r) + 1 producer warp whose lane 0 issues every TMA load and every MMA. Per BN-key tile j (BN = 64 for head dims
-// <= 48, where four CTAs then share an SM - 16 softmax warps - and 128 otherwise, two CTAs per SM):
-//   producer:  S = Q K_j^T           tcgen05.mma M=128 N=BN K=DH -> TMEM columns [0,BN)            -> commit s_full
-//   softmax :  S -> registers (BN fp32 per thread), release S (s_free: the producer may issue S_{j+1} at once),
-//              row max / exp2, P -> fp16 -> shared memory (K-major SW128)                          -> arrive p_full
-//   producer:  O += P V_j, L += P 1  tcgen05.mma M=128 N=DH (+16) K=BN (V MN-major: no transpose)  -> commit pv_done
-// The kernel is bound by the exponentials (16 / cycle / SM against a 128 x 128 x 48 MMA pair of ~400 cycles), so every
-// instruction taken out of the softmax warps counts: the row sum is NOT accumulated by the threads but by the tensor core,
-// as 16 extra accumulator columns L = P x (a tile of ones) next to O, from the same fp16 P the numerator uses.
-// O and L stay in TMEM for the whole key loop. The running maximum is only raised when a row's maximum grows by more than
-// 2^8 (P <= 256 fits fp16; exactness is unaffected because numerator and denominator share the reference maximum); only
-// then does the softmax warp rescale its 32 rows of O | L in TMEM (tcgen05.ld -> multiply -> tcgen05.st) before releasing P.
-// K and V are single-buffered: K_{j+1} is requested the moment S_j has completed and V_{j+1} when P V_j has - both land
-// before the exp-bound softmax of tile j is through; the CTAs sharing the SM cover each other's remaining bubbles.
+// <= 48, where four CTAs share an SM - 16 softmax warps - and 128 otherwise, two CTAs per SM):
+//   producer:  S = Q K_j^T           tcgen05.mma M=128 N=BN K=DH, A/B from shared memory -> TMEM [0,BN)   -> commit s_full
+//   softmax :  S -> registers (BN fp32 per thread), row max, exp2, P -> fp16 pairs -> tcgen05.st back into TMEM columns
+//              [0, BN/2) of the thread's own lane (over its own, already consumed, S)                      -> arrive p_full
+//   producer:  O += P V_j, L += P 1  tcgen05.mma with the A operand (P) read FROM TENSOR MEMORY, B = V_j MN-major straight
+//              from its TMA tile (no transpose) / a tile of ones; then S_{j+1}                             -> commit pv_done
+// P never touches shared memory: the only shared-memory traffic is TMA writes and the MMA's operand reads (the first
+// version staged P through 32 KB of shared memory per tile and was co-limited by the 128 B/cycle shared-memory port).
+// The tensor pipe executes in issue order, so P V_j (reads P) may be followed at once by S_{j+1} (overwrites it).
+// The kernel is bound by the exponentials (16 / cycle / SM; a 128 x 128 x 48 MMA pair is ~400 cycles), so instructions are
+// taken out of the softmax warps wherever possible: the row sum is accumulated by the tensor core as 16 extra accumulator
+// columns L = P x ones, from the same fp16 P the numerator uses. O and L stay in TMEM for the whole key loop; the running
+// maximum is only raised when a row's maximum grows by more than 2^8 (P <= 256 fits fp16; exactness is unaffected because
+// numerator and denominator share the reference maximum); only then does the softmax warp rescale its 32 rows of O | L
+// (tcgen05.ld -> multiply -> tcgen05.st). K and V tiles are double-buffered TMA loads.
 #include <math.h>
 
 #include "tma_common.cuh"
@@ -45,12 +47,11 @@ struct FACfg {
   static constexpr int DHP = T::DHP;
   static constexpr int BN = DHP <= 48 ? 64 : 128;   // keys per tile (UMMA N of S, K extent of P V)
   using TK = TileParts<DH, BN>;       // K / V tiles
-  static constexpr int P_BYTES = (BN / 64) * 16384;         // P [128 q][BN keys] fp16: K-major SW128 parts of 64 keys
   static constexpr int ONES_BYTES = BN * 32;                 // [BN keys][16] fp16 ones (MN-major SW32 part; all 1.0)
-  static constexpr int OFF_Q = 0, OFF_K = T::BYTES, OFF_V = OFF_K + TK::BYTES, OFF_P = OFF_V + TK::BYTES;
-  static constexpr int OFF_ONES = OFF_P + P_BYTES, OFF_BAR = OFF_ONES + ONES_BYTES;
+  static constexpr int OFF_Q = 0, OFF_K = T::BYTES, OFF_V = OFF_K + 2 * TK::BYTES;   // K, V: 2 stages each
+  static constexpr int OFF_ONES = OFF_V + 2 * TK::BYTES, OFF_BAR = OFF_ONES + ONES_BYTES;
   static constexpr int SMEM = OFF_BAR + 128 + 1024;          // + alignment slack (dynamic smem base is 16 B aligned)
-  static constexpr int O_COL = BN;                           // O at TMEM columns [BN, BN + DHP), L at [BN + DHP, + 16)
+  static constexpr int O_COL = BN;                           // S / P at TMEM [0, BN), O at [BN, BN + DHP), L next
   static constexpr int L_COL = BN + DHP;
   static constexpr int ACC_COLS = DHP + 16;                  // O | L
   static constexpr int TCOLS = (BN + ACC_COLS <= 128) ? 128 : ((BN + ACC_COLS <= 256) ? 256 : 512);
@@ -79,24 +80,24 @@ __device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint32_t sA, uint32_t 
   }
 }
 
-// O[128 x DH] (+)= P[128 x BN] V[BN x DH] and L[128 x 16] (+)= P 1: A = K-major SW128 parts (64 keys each) written by
-// threads, B = the V tile read MN-major (its rows are the K dimension) / the tile of ones. One MMA per (k16 step, part).
+// O[128 x DH] (+)= P[128 x BN] V[BN x DH] and L[128 x 16] (+)= P 1: A = P in tensor memory (8 packed columns per k16 step),
+// B = the V tile read MN-major (its rows are the K dimension) / the tile of ones. One MMA per (k16 step, part of B).
 template <int DH>
-__device__ __forceinline__ void issue_pv(uint32_t o_tmem, uint32_t sA, uint32_t sB, uint32_t sOnes, bool accumulate) {
+__device__ __forceinline__ void issue_pv(uint32_t o_tmem, uint32_t p_tmem, uint32_t sB, uint32_t sOnes, bool accumulate) {
   using X = FACfg<DH>;
   using T = typename X::TK;
   const uint32_t idesc64 = umma_idesc_f16(kFM, T::W64, false, true);
   const uint32_t idesc16 = umma_idesc_f16(kFM, 16, false, true);
 #pragma unroll
   for (int ks = 0; ks < X::BN / 16; ++ks) {
-    const uint64_t a = desc_k128(sA + (ks >> 2) * 16384, ks & 3);
+    const uint32_t a = p_tmem + ks * 8;
     const uint32_t acc = (accumulate || ks > 0) ? 1u : 0u;
 #pragma unroll
-    for (int p = 0; p < T::N64; ++p) umma_f16(o_tmem + p * 64, a, desc_mn128(sB + T::part64_off(p), ks), idesc64, acc);
+    for (int p = 0; p < T::N64; ++p) umma_f16_ts(o_tmem + p * 64, a, desc_mn128(sB + T::part64_off(p), ks), idesc64, acc);
 #pragma unroll
     for (int p = 0; p < T::N16; ++p)
-      umma_f16(o_tmem + T::N64 * 64 + p * 16, a, desc_mn32(sB + T::part16_off(p), ks), idesc16, acc);
-    umma_f16(o_tmem + X::DHP, a, desc_mn32(sOnes, ks), idesc16, acc);
+      umma_f16_ts(o_tmem + T::N64 * 64 + p * 16, a, desc_mn32(sB + T::part16_off(p), ks), idesc16, acc);
+    umma_f16_ts(o_tmem + X::DHP, a, desc_mn32(sOnes, ks), idesc16, acc);
   }
 }
 
@@ -114,18 +115,15 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem + X::OFF_Q;
-  uint8_t* sK = smem + X::OFF_K;
-  uint8_t* sV = smem + X::OFF_V;
-  uint8_t* sP = smem + X::OFF_P;
+  uint8_t* sK = smem + X::OFF_K;   // 2 stages
+  uint8_t* sV = smem + X::OFF_V;   // 2 stages
   uint8_t* sOnes = smem + X::OFF_ONES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X::OFF_BAR);
-  uint64_t* bar_q = bars + 0;      // Q landed                       (tx)
-  uint64_t* bar_k = bars + 1;      // K_j landed                     (tx, phase j & 1)
-  uint64_t* bar_v = bars + 2;      // V_j landed                     (tx)
-  uint64_t* s_full = bars + 3;     // S_j in TMEM                    (tcgen05.commit)
-  uint64_t* s_free = bars + 4;     // S_j copied to registers        (4 warp arrivals)
-  uint64_t* p_full = bars + 5;     // P_j in shared memory           (4 warp arrivals)
-  uint64_t* pv_done = bars + 6;    // O += P_j V_j completed         (tcgen05.commit)
+  uint64_t* bar_q = bars + 0;      // Q landed                         (tx)
+  uint64_t* bar_kv = bars + 1;     // [2] K_j and V_j landed in stage j & 1 (tx)
+  uint64_t* s_full = bars + 3;     // S_j in TMEM                      (tcgen05.commit)
+  uint64_t* p_full = bars + 4;     // P_j in TMEM, S_j consumed        (4 warp arrivals)
+  uint64_t* pv_done = bars + 5;    // O += P_j V_j completed           (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -136,8 +134,8 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
   if (warp == 4) {
     tmem_alloc<X::TCOLS>(tmem_slot);
     if (lane == 0) {
-      mbar_init(bar_q, 1), mbar_init(bar_k, 1), mbar_init(bar_v, 1), mbar_init(s_full, 1);
-      mbar_init(s_free, 4), mbar_init(p_full, 4), mbar_init(pv_done, 1);
+      mbar_init(bar_q, 1), mbar_init(bar_kv, 1), mbar_init(bar_kv + 1, 1), mbar_init(s_full, 1);
+      mbar_init(p_full, 4), mbar_init(pv_done, 1);
       fence_mbar_init();
       tma_prefetch_desc(&mq128), tma_prefetch_desc(&mk128), tma_prefetch_desc(&mv128);
     }
@@ -156,36 +154,34 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_q, T::BYTES);
       tma_load_tile<DH>(sQ, &mq128, &mq32, bar_q, q0, h, b);
-      mbar_arrive_expect_tx(bar_k, TK::BYTES);
-      tma_load_tile<DH, BN>(sK, &mk128, &mk32, bar_k, 0, h, b);
-      mbar_arrive_expect_tx(bar_v, TK::BYTES);
-      tma_load_tile<DH, BN>(sV, &mv128, &mv32, bar_v, 0, h, b);
+      for (int j = 0; j < 2 && j < T_tiles; ++j) {
+        mbar_arrive_expect_tx(bar_kv + j, 2 * TK::BYTES);
+        tma_load_tile<DH, BN>(sK + j * TK::BYTES, &mk128, &mk32, bar_kv + j, j * BN, h, b);
+        tma_load_tile<DH, BN>(sV + j * TK::BYTES, &mv128, &mv32, bar_kv + j, j * BN, h, b);
+      }
       mbar_wait(bar_q, 0);
-      mbar_wait(bar_k, 0);
+      mbar_wait(bar_kv, 0);
       tc_fence_after();
       issue_qk<DH>(tmem_base, smem_u32(sQ), smem_u32(sK));
       umma_commit(s_full);
       for (int j = 0; j < T_tiles; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait(s_full, ph);  // S_j completed: the K buffer is free
-        if (j + 1 < T_tiles) {
-          mbar_arrive_expect_tx(bar_k, TK::BYTES);
-          tma_load_tile<DH, BN>(sK, &mk128, &mk32, bar_k, (j + 1) * BN, h, b);
-          mbar_wait(bar_k, ph ^ 1);
-          mbar_wait(s_free, ph);  // every softmax thread holds S_j in registers
+        const uint32_t ph = j & 1, st = j & 1;
+        mbar_wait(p_full, ph);  // every softmax thread has consumed S_j and written P_j
+        tc_fence_after();
+        issue_pv<DH>(tmem_base + X::O_COL, tmem_base, smem_u32(sV + st * TK::BYTES), smem_u32(sOnes), j > 0);
+        umma_commit(pv_done);
+        if (j + 1 < T_tiles) {  // S_{j+1} right behind P V_j (in-order pipe: P_j is read before it is overwritten)
+          const int sn = (j + 1) & 1;
+          mbar_wait(bar_kv + sn, ((j + 1) >> 1) & 1);
           tc_fence_after();
-          issue_qk<DH>(tmem_base, smem_u32(sQ), smem_u32(sK));
+          issue_qk<DH>(tmem_base, smem_u32(sQ), smem_u32(sK + sn * TK::BYTES));
           umma_commit(s_full);
         }
-        mbar_wait(bar_v, ph);
-        mbar_wait(p_full, ph);
-        tc_fence_after();
-        issue_pv<DH>(tmem_base + X::O_COL, smem_u32(sP), smem_u32(sV), smem_u32(sOnes), j > 0);
-        umma_commit(pv_done);
-        if (j + 1 < T_tiles) {
-          mbar_wait(pv_done, ph);  // V buffer (and P buffer) free
-          mbar_arrive_expect_tx(bar_v, TK::BYTES);
-          tma_load_tile<DH, BN>(sV, &mv128, &mv32, bar_v, (j + 1) * BN, h, b);
+        if (j + 2 < T_tiles) {
+          mbar_wait(pv_done, ph);  // K_j / V_j consumed: refill the stage with tile j + 2
+          mbar_arrive_expect_tx(bar_kv + st, 2 * TK::BYTES);
+          tma_load_tile<DH, BN>(sK + st * TK::BYTES, &mk128, &mk32, bar_kv + st, (j + 2) * BN, h, b);
+          tma_load_tile<DH, BN>(sV + st * TK::BYTES, &mv128, &mv32, bar_kv + st, (j + 2) * BN, h, b);
         }
       }
     }
@@ -202,9 +198,6 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
 #pragma unroll
       for (int cc = 0; cc < BN / 32; ++cc) tmem_ld32(lane_addr + cc * 32, s + cc * 32);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_free);
 
       const int kvalid = N - j * BN;  // keys of this tile that exist (>= 1)
       if (kvalid < BN) {
@@ -220,7 +213,6 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
         mx2 = fmaxf(mx2, __uint_as_float(s[i + 2])), mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
       }
       const float mxc = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
-      bool waited_pv = false;
       if (j == 0) {
         m_used = mxc;
       } else {
@@ -230,7 +222,6 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
           const float alpha = ex2_approx(m_used - m_new);
           m_used = m_new;
           mbar_wait(pv_done, ph ^ 1);  // O | L hold tiles 0..j-1
-          waited_pv = true;
           tc_fence_after();
 #pragma unroll
           for (int cc = 0; cc < X::ACC_COLS / 16; ++cc) {
@@ -241,8 +232,6 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
             for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
             tmem_st16(lane_addr + X::O_COL + cc * 16, r);
           }
-          tmem_st_wait();
-          tc_fence_before();
         }
       }
       // p = exp2(s*c - m_used), packed to fp16 pairs in place (s[0 .. BN/2) then hold the BN probabilities)
@@ -253,13 +242,10 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
         const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), c, negm));
         s[i >> 1] = pack_half2(p0, p1);
       }
-      if (j > 0 && !waited_pv) mbar_wait(pv_done, ph ^ 1);  // P_{j-1} consumed: the P buffer is free
 #pragma unroll
-      for (int ch = 0; ch < BN / 8; ++ch) {  // 16-byte chunk ch = keys [8 ch, 8 ch + 8)
-        uint8_t* dst = sP + (ch >> 3) * 16384 + sw128_chunk_off(tid, ch & 7);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(s[4 * ch], s[4 * ch + 1], s[4 * ch + 2], s[4 * ch + 3]);
-      }
-      fence_proxy_async();
+      for (int cc = 0; cc < BN / 64; ++cc) tmem_st32(lane_addr + cc * 32, s + cc * 32);  // P over the consumed S
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }

@@ -39,6 +39,13 @@ inline mc_encode_tiled_fn tensor_map_encoder() {
 inline int make_attn_tensor_map(CUtensorMap* map, const void* base, int DH, int H, int64_t rows, int64_t frames,
                                 int64_t stride_r, int64_t stride_b, int box_e, int box_rows, bool swizzle128) {
   mc_encode_tiled_fn enc = tensor_map_encoder();
+  // The encoder is a DRIVER entry point: it needs the primary context current on the calling thread. A thread that has
+  // not yet made a runtime call (autograd's backward worker on its first node) has none -> CUDA_ERROR_INVALID_CONTEXT.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);  // binds the runtime's primary context to this thread (no-op otherwise)
+    ctx_bound = true;
+  }
   if (!enc) {
     set_error("cuTensorMapEncodeTiled: driver entry point unavailable (cudaGetDriverEntryPoint failed)");
     return -1;
@@ -158,6 +165,28 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
       "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+// D (+)= A B with A in TENSOR MEMORY (fp16 pairs: lane = row m, 32-bit column j = elements k = 2j, 2j + 1; 8 columns per
+// k16 step) and B through a shared-memory descriptor: P / dS tiles never round-trip through shared memory.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

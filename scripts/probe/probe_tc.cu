@@ -1,7 +1,7 @@
 // Hardware probes for the building blocks of csrc/spatial_attn_tc.cu (TEST / BRING-UP TOOL, not product code):
 // each probe isolates one feature (tensor-map TMA with 128B / 32B swizzle, swizzled K-major / MN-major UMMA descriptors,
 // MN-major A operands, tcgen05.st) and checks it against a CPU computation. One probe per process (a faulting probe must
-// not poison the next):   probe_tc <name>      names: tma128 tma32 qk40 qk80 qk160 pv40 pv80 pv160 amn40 amn80 tmemst
+// not poison the next):   probe_tc <name>      names: tma128 tma32 qk40 qk80 qk160 pv40 pv80 pv160 ts40 ts80 ts160 amn40 amn80 tmemst
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I motionclone_b200/csrc scripts/probe/probe_tc.cu
 #include <cstdio>
 #include <cstdlib>
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) k_mma(const __grid_constant__ CUtensorMap
     mbar_init(bar, 1), mbar_init(bar2, 1);
     fence_mbar_init();
   }
-  if (mode >= 1) {  // thread = row: write its 128 fp16 as two K-major SW128 parts
+  if (mode >= 1 && mode != 3) {  // thread = row: write its 128 fp16 as two K-major SW128 parts
     const uint4* src = reinterpret_cast<const uint4*>(pmat + (size_t)tid * 128);
     for (int ch = 0; ch < 16; ++ch) *reinterpret_cast<uint4*>(sP + (ch >> 3) * 16384 + sw128_chunk_off(tid, ch & 7)) = src[ch];
   }
@@ -81,6 +81,18 @@ __global__ void __launch_bounds__(128) k_mma(const __grid_constant__ CUtensorMap
   __syncthreads();
   tc_fence_after();
   const uint32_t tb = *slot;
+  if (mode == 3) {  // thread = row = TMEM lane: its 128 fp16 as 64 packed columns at [256, 320)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(pmat + (size_t)tid * 128);
+    uint32_t r[32];
+    for (int half = 0; half < 2; ++half) {
+      for (int i = 0; i < 32; ++i) r[i] = src[half * 32 + i];
+      tmem_st32(tb + ((uint32_t)(warp * 32) << 16) + 256 + half * 32, r);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   if (tid == 0) {
     if (mode == 0) {
       mbar_arrive_expect_tx(bar, 2 * T::BYTES);
@@ -104,6 +116,15 @@ __global__ void __launch_bounds__(128) k_mma(const __grid_constant__ CUtensorMap
       for (int p = 0; p < T::N16; ++p) {
         umma_f16(tb, desc_k32(smem_u32(sA) + T::part16_off(p)), desc_k32(smem_u32(sB) + T::part16_off(p)), idesc, acc);
         acc = 1;
+      }
+    } else if (mode == 3) {
+      const uint32_t id64 = umma_idesc_f16(128, T::W64, false, true);
+      const uint32_t id16 = umma_idesc_f16(128, 16, false, true);
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t a = tb + 256 + ks * 8;  // 8 packed columns per k16 step
+        const uint32_t acc = ks > 0;
+        for (int p = 0; p < T::N64; ++p) umma_f16_ts(tb + p * 64, a, desc_mn128(smem_u32(sB) + T::part64_off(p), ks), id64, acc);
+        for (int p = 0; p < T::N16; ++p) umma_f16_ts(tb + T::N64 * 64 + p * 16, a, desc_mn32(smem_u32(sB) + T::part16_off(p), ks), id16, acc);
       }
     } else {
       const uint32_t id64 = umma_idesc_f16(128, T::W64, mode == 2, true);
@@ -224,7 +245,7 @@ static int run_mma(int mode, const char* name) {
   using T = TileParts<DH>;
   Synth t(128, 2, DH, 1);
   CUtensorMap a128, a32, b128, b32;
-  const int wa = 0, wb = mode == 0 ? 1 : (mode == 1 ? 2 : 1);  // mode0: Q,K  mode1: V  mode2: K
+  const int wa = 0, wb = mode == 0 ? 1 : (mode == 2 ? 1 : 2);  // mode0: Q,K  mode1/3: V  mode2: K
   int rc = make_attn_tensor_map(&a128, t.ptr(wa), DH, 2, 128, 1, t.sr, t.sb, 64, 128, true);
   rc |= make_attn_tensor_map(&b128, t.ptr(wb), DH, 2, 128, 1, t.sr, t.sb, 64, 128, true);
   a32 = a128, b32 = b128;
@@ -260,7 +281,7 @@ static int run_mma(int mode, const char* name) {
       double want = 0;
       if (mode == 0) {
         for (int e = 0; e < DH; ++e) want += (double)t.at(0, 0, m, 1, e) * t.at(1, 0, n, 1, e);
-      } else if (mode == 1) {
+      } else if (mode == 1 || mode == 3) {
         for (int j = 0; j < 128; ++j) want += (double)h2f(P[m * 128 + j]) * t.at(2, 0, j, 1, n);
       } else {  // D[m][n] = sum_k X^T[k][m] * K[k][n]
         for (int j = 0; j < 128; ++j) want += (double)h2f(P[j * 128 + m]) * t.at(1, 0, j, 1, n);
@@ -304,6 +325,9 @@ int main(int argc, char** argv) {
   if (n == "pv80") return run_mma<80>(1, "pv80");
   if (n == "pv160") return run_mma<160>(1, "pv160");
   if (n == "pv16") return run_mma<16>(1, "pv16");
+  if (n == "ts40") return run_mma<40>(3, "ts40");
+  if (n == "ts80") return run_mma<80>(3, "ts80");
+  if (n == "ts160") return run_mma<160>(3, "ts160");
   if (n == "amn40") return run_mma<40>(2, "amn40");
   if (n == "amn80") return run_mma<80>(2, "amn80");
   if (n == "tmemst") return run_tmemst();
