@@ -11,8 +11,13 @@
 //                -> P^T, dS^T -> smem -> dV += P^T dO, dK += dS^T Q
 // Both kernels: 8 compute warps (thread = TMEM lane = tile row, the two warps that share a lane quarter split the 64
 // columns) + 1 producer warp whose lane 0 issues every TMA load and MMA; accumulators in TMEM; 2 CTAs per SM where the
-// TMEM budget allows. Every [rows][DH] tile serves two GEMMs through two descriptors - K-major where DH is contracted
-// (S, dP), MN-major where the rows are (dS K, P^T dO, dS^T Q) - so nothing is transposed or copied twice. There are no
+// TMEM budget allows. Every streamed [rows][DH] tile serves two GEMMs through two descriptors - K-major where DH is
+// contracted (S, dP), MN-major where the rows are (dS K, P^T dO, dS^T Q) - so nothing is transposed or copied twice.
+// The tiles the threads produce (dS, P^T, dS^T) never touch shared memory: they go back into tensor memory as fp16 pairs
+// (tcgen05.st) and are the A operands of the next MMAs (tcgen05.mma with A in TMEM); for head dims <= 48 the resident
+// operand tiles (Q, dO in the dQ kernel, V in the dK/dV kernel) are moved into tensor memory once, too. An MMA whose A
+// operand comes from shared memory re-reads 4 KB of it per k16 step - that traffic, not the math, bounded the first
+// version (ncu: tensor pipe 47-52 % busy at ~70 cycles per MMA). There are no
 // masks: rows past the end of the sequence are zero-filled by the TMA unit, and a zero K / V / Q / dO row contributes
 // nothing to any of the sums (the padded statistics keep every intermediate finite). The two-kernel split recomputes S and
 // dP once more than a fused kernel would but needs no atomics on dQ: results are deterministic.
@@ -72,25 +77,26 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __half* __rest
   dsc[dst] = acc * scale;
 }
 
-// D[128 x DH] (+)= A[128 x 64] B[64 x DH]: A = one K-major SW128 part written by threads, B = a 64-row tile read MN-major
-template <int DH>
-__device__ __forceinline__ void issue_ab64(uint32_t d_tmem, uint32_t sA, uint32_t sB, bool accumulate) {
+// D[128 x DH] (+)= A[128 x 64] B[64 x DH]: A = fp16 pairs in TENSOR MEMORY (P^T / dS / dS^T written there by the compute
+// threads; k16 step ks at a_tmem(ks)), B = a 64-row tile read MN-major
+template <int DH, typename AddrFn>
+__device__ __forceinline__ void issue_ab64_ts(uint32_t d_tmem, AddrFn a_tmem, uint32_t sB, bool accumulate) {
   using T = TileParts<DH, kBT>;
   const uint32_t idesc64 = umma_idesc_f16(128, T::W64, false, true);
   const uint32_t idesc16 = umma_idesc_f16(128, 16, false, true);
 #pragma unroll
   for (int ks = 0; ks < kBT / 16; ++ks) {
-    const uint64_t a = desc_k128(sA, ks);
+    const uint32_t a = a_tmem(ks);
     const uint32_t acc = (accumulate || ks > 0) ? 1u : 0u;
 #pragma unroll
-    for (int p = 0; p < T::N64; ++p) umma_f16(d_tmem + p * 64, a, desc_mn128(sB + T::part64_off(p), ks), idesc64, acc);
+    for (int p = 0; p < T::N64; ++p) umma_f16_ts(d_tmem + p * 64, a, desc_mn128(sB + T::part64_off(p), ks), idesc64, acc);
 #pragma unroll
     for (int p = 0; p < T::N16; ++p)
-      umma_f16(d_tmem + T::N64 * 64 + p * 16, a, desc_mn32(sB + T::part16_off(p), ks), idesc16, acc);
+      umma_f16_ts(d_tmem + T::N64 * 64 + p * 16, a, desc_mn32(sB + T::part16_off(p), ks), idesc16, acc);
   }
 }
 
-// D[128 x 64] = A[128 x DH] B[64 x DH]^T: A a 128-row tile, B a 64-row tile, both K-major
+// D[128 x 64] = A[128 x DH] B[64 x DH]^T: B a 64-row tile (K-major); A a 128-row tile, K-major in shared memory ...
 template <int DH>
 __device__ __forceinline__ void issue_qk64(uint32_t d_tmem, uint32_t sA, uint32_t sB) {
   using TA = TileParts<DH, 128>;
@@ -110,26 +116,38 @@ __device__ __forceinline__ void issue_qk64(uint32_t d_tmem, uint32_t sA, uint32_
     acc = 1;
   }
 }
+// ... or resident in tensor memory (head dims <= 48: DHP / 2 packed columns at a_tmem, see smem_row_to_tmem)
+template <int DH>
+__device__ __forceinline__ void issue_qk64_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t sB) {
+  using TB = TileParts<DH, kBT>;
+  static_assert(TB::N64 == 1 && TB::N16 == 0, "tensor-memory A operands: head dims <= 48");
+  const uint32_t idesc = umma_idesc_f16(128, kBT, false, false);
+#pragma unroll
+  for (int ks = 0; ks < TB::KS64; ++ks) umma_f16_ts(d_tmem, a_tmem + ks * 8, desc_k128(sB, ks), idesc, ks > 0 ? 1u : 0u);
+}
 
 template <int DH>
 struct FABwdCfg {
   using TA = TileParts<DH, 128>;   // resident tiles
   using TB = TileParts<DH, kBT>;   // streamed tiles
   static constexpr int DHP = TA::DHP;
-  static constexpr int X_BYTES = 128 * 128;  // one K-major SW128 part [128 rows][64] written by threads
-  // dQ kernel: Q, dO resident; K, V double-buffered; dS
+  static constexpr bool AT = DHP <= 48;   // resident operand tiles live in tensor memory as A operands
+  static constexpr int KP = DHP / 2;      // packed columns of a resident [128][DHP] fp16 tile
+  // dQ kernel. shared memory: Q, dO (only staging when AT); K, V double-buffered.
   static constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TA::BYTES, DQ_OFF_K = 2 * TA::BYTES, DQ_OFF_V = DQ_OFF_K + 2 * TB::BYTES;
-  static constexpr int DQ_OFF_DS = DQ_OFF_V + 2 * TB::BYTES, DQ_OFF_BAR = DQ_OFF_DS + X_BYTES;
-  static constexpr int DQ_SMEM = DQ_OFF_BAR + 128 + 1024;
-  static constexpr int DQ_COL = 128;  // S [0,64) dP [64,128) dQ [128, 128 + DHP)
-  static constexpr int DQ_TCOLS = (128 + DHP <= 256) ? 256 : 512;
+  static constexpr int DQ_OFF_BAR = DQ_OFF_V + 2 * TB::BYTES, DQ_SMEM = DQ_OFF_BAR + 128 + 1024;
+  // tensor memory: S [0,64) dP [64,128) dS(fp16 pairs) [128,160) dQ [160,160+DHP) [Q, dO packed when AT]
+  static constexpr int DQ_DS = 128, DQ_ACC = 160, DQ_QT = 160 + DHP, DQ_DOT = DQ_QT + KP;
+  static constexpr int DQ_NEED = AT ? DQ_DOT + KP : DQ_ACC + DHP;
+  static constexpr int DQ_TCOLS = DQ_NEED <= 256 ? 256 : 512;
   static constexpr int DQ_CTAS = (DQ_TCOLS == 256 && 2 * DQ_SMEM <= 227 * 1024) ? 2 : 1;
-  // dKV kernel: K, V resident; Q, dO double-buffered; P^T, dS^T
+  // dKV kernel. shared memory: K, V resident; Q, dO double-buffered.
   static constexpr int KV_OFF_K = 0, KV_OFF_V = TA::BYTES, KV_OFF_Q = 2 * TA::BYTES, KV_OFF_DO = KV_OFF_Q + 2 * TB::BYTES;
-  static constexpr int KV_OFF_PT = KV_OFF_DO + 2 * TB::BYTES, KV_OFF_DST = KV_OFF_PT + X_BYTES;
-  static constexpr int KV_OFF_BAR = KV_OFF_DST + X_BYTES, KV_SMEM = KV_OFF_BAR + 128 + 1024;
-  static constexpr int DV_COL = 128, DK_COL = 128 + DHP;  // S^T [0,64) dP^T [64,128) dV, dK
-  static constexpr int KV_TCOLS = (128 + 2 * DHP <= 256) ? 256 : 512;
+  static constexpr int KV_OFF_BAR = KV_OFF_DO + 2 * TB::BYTES, KV_SMEM = KV_OFF_BAR + 128 + 1024;
+  // tensor memory: S^T [0,64) dP^T [64,128) (P^T / dS^T are written back over them as fp16 pairs) dV, dK [V packed when AT]
+  static constexpr int DV_COL = 128, DK_COL = 128 + DHP, KV_VT = 128 + 2 * DHP;
+  static constexpr int KV_NEED = AT ? KV_VT + KP : KV_VT;
+  static constexpr int KV_TCOLS = KV_NEED <= 256 ? 256 : 512;
   static constexpr int KV_CTAS = (KV_TCOLS == 256 && 2 * KV_SMEM <= 227 * 1024) ? 2 : 1;
 };
 
@@ -181,14 +199,14 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
   uint8_t* sDO = smem + X::DQ_OFF_DO;
   uint8_t* sK = smem + X::DQ_OFF_K;   // 2 stages
   uint8_t* sV = smem + X::DQ_OFF_V;   // 2 stages
-  uint8_t* sDS = smem + X::DQ_OFF_DS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X::DQ_OFF_BAR);
   uint64_t* bar_q = bars + 0;        // Q and dO landed
   uint64_t* bar_kv = bars + 1;       // [2] K_j, V_j landed in stage j & 1
   uint64_t* sdp_full = bars + 3;     // S_j, dP_j in TMEM
   uint64_t* sdp_free = bars + 4;     // copied to registers (8 warp arrivals)
-  uint64_t* ds_full = bars + 5;      // dS_j in shared memory (8 warp arrivals)
+  uint64_t* ds_full = bars + 5;      // dS_j in TMEM (8 warp arrivals)
   uint64_t* dq_done = bars + 6;      // dQ += dS_j K_j completed
+  uint64_t* a_ready = bars + 7;      // Q, dO copied into tensor memory (8 warp arrivals; AT only)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -201,6 +219,7 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
     if (lane == 0) {
       mbar_init(bar_q, 1), mbar_init(bar_kv, 1), mbar_init(bar_kv + 1, 1), mbar_init(sdp_full, 1);
       mbar_init(sdp_free, kBComputeWarps), mbar_init(ds_full, kBComputeWarps), mbar_init(dq_done, 1);
+      mbar_init(a_ready, kBComputeWarps);
       fence_mbar_init();
     }
   }
@@ -211,6 +230,15 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
 
   if (warp == kBComputeWarps) {
     if (lane == 0) {
+      auto issue_sdp = [&](int stage) {
+        if constexpr (X::AT) {
+          issue_qk64_ts<DH>(tmem_base, tmem_base + X::DQ_QT, smem_u32(sK + stage * TB::BYTES));
+          issue_qk64_ts<DH>(tmem_base + 64, tmem_base + X::DQ_DOT, smem_u32(sV + stage * TB::BYTES));
+        } else {
+          issue_qk64<DH>(tmem_base, smem_u32(sQ), smem_u32(sK + stage * TB::BYTES));
+          issue_qk64<DH>(tmem_base + 64, smem_u32(sDO), smem_u32(sV + stage * TB::BYTES));
+        }
+      };
       mbar_arrive_expect_tx(bar_q, 2 * TA::BYTES);
       tma_load_tile<DH, 128>(sQ, &mq128, &mq32, bar_q, q0, h, b);
       tma_load_tile<DH, 128>(sDO, &mdo128, &mdo32, bar_q, q0, h, b);
@@ -219,11 +247,11 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
         tma_load_tile<DH, kBT>(sK + j * TB::BYTES, &mk128, &mk32, bar_kv + j, j * kBT, h, b);
         tma_load_tile<DH, kBT>(sV + j * TB::BYTES, &mv128, &mv32, bar_kv + j, j * kBT, h, b);
       }
-      mbar_wait(bar_q, 0);
+      if constexpr (X::AT) mbar_wait(a_ready, 0);
+      else mbar_wait(bar_q, 0);
       mbar_wait(bar_kv, 0);
       tc_fence_after();
-      issue_qk64<DH>(tmem_base, smem_u32(sQ), smem_u32(sK));
-      issue_qk64<DH>(tmem_base + 64, smem_u32(sDO), smem_u32(sV));
+      issue_sdp(0);
       umma_commit(sdp_full);
       for (int j = 0; j < T_tiles; ++j) {
         const uint32_t ph = j & 1, st = j & 1;
@@ -232,13 +260,13 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
           mbar_wait(bar_kv + sn, ((j + 1) >> 1) & 1);
           mbar_wait(sdp_free, ph);
           tc_fence_after();
-          issue_qk64<DH>(tmem_base, smem_u32(sQ), smem_u32(sK + sn * TB::BYTES));
-          issue_qk64<DH>(tmem_base + 64, smem_u32(sDO), smem_u32(sV + sn * TB::BYTES));
+          issue_sdp(sn);
           umma_commit(sdp_full);
         }
         mbar_wait(ds_full, ph);
         tc_fence_after();
-        issue_ab64<DH>(tmem_base + X::DQ_COL, smem_u32(sDS), smem_u32(sK + st * TB::BYTES), j > 0);
+        issue_ab64_ts<DH>(tmem_base + X::DQ_ACC, [&](int ks) { return tmem_base + X::DQ_DS + ks * 8; },
+                          smem_u32(sK + st * TB::BYTES), j > 0);
         umma_commit(dq_done);
         if (j + 2 < T_tiles) {
           mbar_wait(dq_done, ph);  // K_j / V_j consumed: refill the stage with tile j + 2
@@ -252,6 +280,14 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
     const int rq = warp & 3, hh = warp >> 2;  // TMEM lane quarter, column half
     const int r = rq * 32 + lane;             // tile row = TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(rq * 32) << 16);
+    if constexpr (X::AT) {  // Q (column half 0) and dO (column half 1) rows -> tensor memory, once
+      mbar_wait(bar_q, 0);
+      smem_row_to_tmem<X::DHP>(hh == 0 ? sQ : sDO, r, lane_addr + (hh == 0 ? X::DQ_QT : X::DQ_DOT));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    }
     const int row = q0 + r;
     const bool rvalid = row < N;
     const int64_t srow = ((int64_t)b * prm.H + h) * prm.Npad + (rvalid ? row : 0);
@@ -275,12 +311,13 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
         const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), c, nl2));
         s[i >> 1] = pack_half2(p0 * fmaf(__uint_as_float(dp[i]), sc, nD), p1 * fmaf(__uint_as_float(dp[i + 1]), sc, nD));
       }
-      if (j > 0) mbar_wait(dq_done, ph ^ 1);  // dS_{j-1} consumed
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
-        *reinterpret_cast<uint4*>(sDS + sw128_chunk_off(r, hh * 4 + ch)) =
-            make_uint4(s[4 * ch], s[4 * ch + 1], s[4 * ch + 2], s[4 * ch + 3]);
-      fence_proxy_async();
+      if (j > 0) {
+        mbar_wait(dq_done, ph ^ 1);  // dS_{j-1} consumed by its MMA
+        tc_fence_after();
+      }
+      tmem_st16(lane_addr + X::DQ_DS + hh * 16, s);  // keys [32 hh, 32 hh + 32) = packed columns [16 hh, 16 hh + 16)
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
     }
@@ -288,7 +325,7 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
     tc_fence_after();
     int c0, ncol;
     half_cols<X::DHP>(hh, c0, ncol);
-    store_cols_from_tmem<DH>(lane_addr + X::DQ_COL, prm.dq + (int64_t)b * prm.g_sb + (int64_t)row * prm.g_sr + h * DH, rvalid,
+    store_cols_from_tmem<DH>(lane_addr + X::DQ_ACC, prm.dq + (int64_t)b * prm.g_sb + (int64_t)row * prm.g_sr + h * DH, rvalid,
                              c0, ncol);
   }
   tc_fence_before();
@@ -316,15 +353,13 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
   uint8_t* sV = smem + X::KV_OFF_V;
   uint8_t* sQ = smem + X::KV_OFF_Q;    // 2 stages
   uint8_t* sDO = smem + X::KV_OFF_DO;  // 2 stages
-  uint8_t* sPT = smem + X::KV_OFF_PT;
-  uint8_t* sDST = smem + X::KV_OFF_DST;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X::KV_OFF_BAR);
   uint64_t* bar_kv = bars + 0;      // K, V landed
   uint64_t* bar_q = bars + 1;       // [2] Q_i, dO_i landed in stage i & 1
   uint64_t* st_full = bars + 3;     // S^T_i, dP^T_i in TMEM
-  uint64_t* st_free = bars + 4;     // copied to registers (8 warp arrivals)
-  uint64_t* pt_full = bars + 5;     // P^T_i, dS^T_i in shared memory (8 warp arrivals)
-  uint64_t* dkv_done = bars + 6;    // dV, dK updates of tile i completed
+  uint64_t* pt_full = bars + 4;     // P^T_i, dS^T_i written back to TMEM, S^T_i / dP^T_i consumed (8 warp arrivals)
+  uint64_t* dkv_done = bars + 5;    // dV, dK updates of tile i completed
+  uint64_t* a_ready = bars + 6;     // V copied into tensor memory (4 warp arrivals; AT only)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -336,7 +371,7 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
     tmem_alloc<X::KV_TCOLS>(tmem_slot);
     if (lane == 0) {
       mbar_init(bar_kv, 1), mbar_init(bar_q, 1), mbar_init(bar_q + 1, 1), mbar_init(st_full, 1);
-      mbar_init(st_free, kBComputeWarps), mbar_init(pt_full, kBComputeWarps), mbar_init(dkv_done, 1);
+      mbar_init(pt_full, kBComputeWarps), mbar_init(dkv_done, 1), mbar_init(a_ready, 4);
       fence_mbar_init();
     }
   }
@@ -344,9 +379,17 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // k16 step ks of a 64-query A operand written back by the two column halves: queries [32 hh, 32 hh + 32) sit in the
+  // packed columns [32 hh, 32 hh + 16) of the region their S^T / dP^T values came from
+  auto a_cols = [](int ks) { return (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8); };
 
   if (warp == kBComputeWarps) {
     if (lane == 0) {
+      auto issue_st = [&](int stage) {
+        issue_qk64<DH>(tmem_base, smem_u32(sK), smem_u32(sQ + stage * TB::BYTES));
+        if constexpr (X::AT) issue_qk64_ts<DH>(tmem_base + 64, tmem_base + X::KV_VT, smem_u32(sDO + stage * TB::BYTES));
+        else issue_qk64<DH>(tmem_base + 64, smem_u32(sV), smem_u32(sDO + stage * TB::BYTES));
+      };
       mbar_arrive_expect_tx(bar_kv, 2 * TA::BYTES);
       tma_load_tile<DH, 128>(sK, &mk128, &mk32, bar_kv, k0, h, b);
       tma_load_tile<DH, 128>(sV, &mv128, &mv32, bar_kv, k0, h, b);
@@ -356,27 +399,27 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
         tma_load_tile<DH, kBT>(sDO + i * TB::BYTES, &mdo128, &mdo32, bar_q + i, i * kBT, h, b);
       }
       mbar_wait(bar_kv, 0);
+      if constexpr (X::AT) mbar_wait(a_ready, 0);
       mbar_wait(bar_q, 0);
       tc_fence_after();
-      issue_qk64<DH>(tmem_base, smem_u32(sK), smem_u32(sQ));
-      issue_qk64<DH>(tmem_base + 64, smem_u32(sV), smem_u32(sDO));
+      issue_st(0);
       umma_commit(st_full);
       for (int i = 0; i < T_tiles; ++i) {
         const uint32_t ph = i & 1, st = i & 1;
-        if (i + 1 < T_tiles) {
+        mbar_wait(pt_full, ph);  // P^T_i, dS^T_i in tensor memory (every thread has consumed S^T_i, dP^T_i)
+        tc_fence_after();
+        issue_ab64_ts<DH>(tmem_base + X::DV_COL, [&](int ks) { return tmem_base + a_cols(ks); },
+                          smem_u32(sDO + st * TB::BYTES), i > 0);
+        issue_ab64_ts<DH>(tmem_base + X::DK_COL, [&](int ks) { return tmem_base + 64 + a_cols(ks); },
+                          smem_u32(sQ + st * TB::BYTES), i > 0);
+        umma_commit(dkv_done);
+        if (i + 1 < T_tiles) {  // next S^T, dP^T right behind (in-order pipe: P^T_i / dS^T_i are read before the overwrite)
           const int sn = (i + 1) & 1;
           mbar_wait(bar_q + sn, ((i + 1) >> 1) & 1);
-          mbar_wait(st_free, ph);
           tc_fence_after();
-          issue_qk64<DH>(tmem_base, smem_u32(sK), smem_u32(sQ + sn * TB::BYTES));
-          issue_qk64<DH>(tmem_base + 64, smem_u32(sV), smem_u32(sDO + sn * TB::BYTES));
+          issue_st(sn);
           umma_commit(st_full);
         }
-        mbar_wait(pt_full, ph);
-        tc_fence_after();
-        issue_ab64<DH>(tmem_base + X::DV_COL, smem_u32(sPT), smem_u32(sDO + st * TB::BYTES), i > 0);
-        issue_ab64<DH>(tmem_base + X::DK_COL, smem_u32(sDST), smem_u32(sQ + st * TB::BYTES), i > 0);
-        umma_commit(dkv_done);
         if (i + 2 < T_tiles) {
           mbar_wait(dkv_done, ph);
           mbar_arrive_expect_tx(bar_q + st, 2 * TB::BYTES);
@@ -389,6 +432,16 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
     const int rq = warp & 3, hh = warp >> 2;
     const int r = rq * 32 + lane;  // key row of the tile = TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(rq * 32) << 16);
+    if constexpr (X::AT) {
+      if (hh == 0) {  // V rows -> tensor memory, once
+        mbar_wait(bar_kv, 0);
+        smem_row_to_tmem<X::DHP>(sV, r, lane_addr + X::KV_VT);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+      }
+    }
     const int row = k0 + r;
     const float c = prm.scale_log2e, sc = prm.scale;
     // per-QUERY statistics of the streamed tile: identical addresses for every thread of a warp (broadcast loads), 16-byte
@@ -403,9 +456,6 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
       tmem_ld32(lane_addr + hh * 32, s);
       tmem_ld32(lane_addr + 64 + hh * 32, dp);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(st_free);
 #pragma unroll
       for (int g = 0; g < 8; ++g) {  // 4 queries per step
         const float4 lq = __ldg(l4 + i * 16 + g), dq4 = __ldg(d4 + i * 16 + g);
@@ -420,14 +470,11 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
         s[2 * g] = pack_half2(p0, p1), s[2 * g + 1] = pack_half2(p2, p3);
         dp[2 * g] = pack_half2(e0, e1), dp[2 * g + 1] = pack_half2(e2, e3);
       }
-      if (i > 0) mbar_wait(dkv_done, ph ^ 1);
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const uint32_t off = sw128_chunk_off(r, hh * 4 + ch);
-        *reinterpret_cast<uint4*>(sPT + off) = make_uint4(s[4 * ch], s[4 * ch + 1], s[4 * ch + 2], s[4 * ch + 3]);
-        *reinterpret_cast<uint4*>(sDST + off) = make_uint4(dp[4 * ch], dp[4 * ch + 1], dp[4 * ch + 2], dp[4 * ch + 3]);
-      }
-      fence_proxy_async();
+      // P^T / dS^T of this thread's 32 queries: fp16 pairs over the first half of the columns its own values came from
+      tmem_st16(lane_addr + hh * 32, s);
+      tmem_st16(lane_addr + 64 + hh * 32, dp);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pt_full);
     }

@@ -47,13 +47,15 @@ struct FACfg {
   static constexpr int DHP = T::DHP;
   static constexpr int BN = DHP <= 48 ? 64 : 128;   // keys per tile (UMMA N of S, K extent of P V)
   using TK = TileParts<DH, BN>;       // K / V tiles
-  static constexpr int ONES_BYTES = BN * 32;                 // [BN keys][16] fp16 ones (MN-major SW32 part; all 1.0)
+  // Row sums: when the head dim leaves zero-padded columns in the V tile (DH = 40 -> 48), column DH of V is set to 1.0
+  // after every TMA load, so accumulator column DH of O = P V IS the row sum (from the same fp16 P as the numerator, at no
+  // extra MMA and no extra instruction in the softmax warps). Otherwise the softmax threads add their probabilities.
+  static constexpr bool PAD_SUM = DHP > DH && DH < 64;
   static constexpr int OFF_Q = 0, OFF_K = T::BYTES, OFF_V = OFF_K + 2 * TK::BYTES;   // K, V: 2 stages each
-  static constexpr int OFF_ONES = OFF_V + 2 * TK::BYTES, OFF_BAR = OFF_ONES + ONES_BYTES;
+  static constexpr int OFF_BAR = OFF_V + 2 * TK::BYTES;
   static constexpr int SMEM = OFF_BAR + 128 + 1024;          // + alignment slack (dynamic smem base is 16 B aligned)
-  static constexpr int O_COL = BN;                           // S / P at TMEM [0, BN), O at [BN, BN + DHP), L next
-  static constexpr int L_COL = BN + DHP;
-  static constexpr int ACC_COLS = DHP + 16;                  // O | L
+  static constexpr int O_COL = BN;                           // S / P at TMEM [0, BN), O at [BN, BN + DHP)
+  static constexpr int ACC_COLS = DHP;
   static constexpr int TCOLS = (BN + ACC_COLS <= 128) ? 128 : ((BN + ACC_COLS <= 256) ? 256 : 512);
   static constexpr int CTAS_TMEM = 512 / TCOLS, CTAS_SMEM = (227 * 1024) / SMEM;
   static constexpr int CTAS_PER_SM = CTAS_TMEM < CTAS_SMEM ? CTAS_TMEM : (CTAS_SMEM < 1 ? 1 : CTAS_SMEM);
@@ -80,10 +82,10 @@ __device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint32_t sA, uint32_t 
   }
 }
 
-// O[128 x DH] (+)= P[128 x BN] V[BN x DH] and L[128 x 16] (+)= P 1: A = P in tensor memory (8 packed columns per k16 step),
-// B = the V tile read MN-major (its rows are the K dimension) / the tile of ones. One MMA per (k16 step, part of B).
+// O[128 x DH] (+)= P[128 x BN] V[BN x DH]: A = P in tensor memory (8 packed columns per k16 step), B = the V tile read
+// MN-major (its rows are the K dimension). One MMA per (k16 step, part of B).
 template <int DH>
-__device__ __forceinline__ void issue_pv(uint32_t o_tmem, uint32_t p_tmem, uint32_t sB, uint32_t sOnes, bool accumulate) {
+__device__ __forceinline__ void issue_pv(uint32_t o_tmem, uint32_t p_tmem, uint32_t sB, bool accumulate) {
   using X = FACfg<DH>;
   using T = typename X::TK;
   const uint32_t idesc64 = umma_idesc_f16(kFM, T::W64, false, true);
@@ -97,8 +99,18 @@ __device__ __forceinline__ void issue_pv(uint32_t o_tmem, uint32_t p_tmem, uint3
 #pragma unroll
     for (int p = 0; p < T::N16; ++p)
       umma_f16_ts(o_tmem + T::N64 * 64 + p * 16, a, desc_mn32(sB + T::part16_off(p), ks), idesc16, acc);
-    umma_f16_ts(o_tmem + X::DHP, a, desc_mn32(sOnes, ks), idesc16, acc);
   }
+}
+
+// all lanes of the producer warp: element DH of every key row of a landed V tile := 1.0 (see FACfg::PAD_SUM)
+template <int DH>
+__device__ __forceinline__ void write_v_ones(uint8_t* sVstage, int lane) {
+  using X = FACfg<DH>;
+  constexpr int ch = DH / 8;  // the 16-byte chunk holding elements [DH, DH + 8): zero-filled by the TMA unit
+  for (int r = lane; r < X::BN; r += 32)
+    *reinterpret_cast<uint4*>(sVstage + sw128_chunk_off(r, ch)) = make_uint4(0x00003C00u, 0u, 0u, 0u);
+  fence_proxy_async();
+  __syncwarp();
 }
 
 template <int DH>
@@ -117,7 +129,6 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
   uint8_t* sQ = smem + X::OFF_Q;
   uint8_t* sK = smem + X::OFF_K;   // 2 stages
   uint8_t* sV = smem + X::OFF_V;   // 2 stages
-  uint8_t* sOnes = smem + X::OFF_ONES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X::OFF_BAR);
   uint64_t* bar_q = bars + 0;      // Q landed                         (tx)
   uint64_t* bar_kv = bars + 1;     // [2] K_j and V_j landed in stage j & 1 (tx)
@@ -139,10 +150,6 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
       fence_mbar_init();
       tma_prefetch_desc(&mq128), tma_prefetch_desc(&mk128), tma_prefetch_desc(&mv128);
     }
-  } else {
-    for (int i = tid; i < X::ONES_BYTES / 16; i += 128)  // fp16 1.0 everywhere: any swizzle of it is itself
-      reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
-    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -150,7 +157,7 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    // ================= producer: TMA + MMA issue (one thread) =================
+    // ================= producer warp: lane 0 issues every TMA load and MMA =================
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_q, T::BYTES);
       tma_load_tile<DH>(sQ, &mq128, &mq32, bar_q, q0, h, b);
@@ -159,37 +166,48 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
         tma_load_tile<DH, BN>(sK + j * TK::BYTES, &mk128, &mk32, bar_kv + j, j * BN, h, b);
         tma_load_tile<DH, BN>(sV + j * TK::BYTES, &mv128, &mv32, bar_kv + j, j * BN, h, b);
       }
-      mbar_wait(bar_q, 0);
-      mbar_wait(bar_kv, 0);
+    }
+    mbar_wait(bar_q, 0);
+    mbar_wait(bar_kv, 0);
+    if constexpr (X::PAD_SUM) write_v_ones<DH>(sV, lane);
+    if (lane == 0) {
       tc_fence_after();
       issue_qk<DH>(tmem_base, smem_u32(sQ), smem_u32(sK));
       umma_commit(s_full);
-      for (int j = 0; j < T_tiles; ++j) {
-        const uint32_t ph = j & 1, st = j & 1;
-        mbar_wait(p_full, ph);  // every softmax thread has consumed S_j and written P_j
+    }
+    for (int j = 0; j < T_tiles; ++j) {
+      const uint32_t ph = j & 1, st = j & 1;
+      mbar_wait(p_full, ph);  // every softmax thread has consumed S_j and written P_j
+      if (lane == 0) {
         tc_fence_after();
-        issue_pv<DH>(tmem_base + X::O_COL, tmem_base, smem_u32(sV + st * TK::BYTES), smem_u32(sOnes), j > 0);
+        issue_pv<DH>(tmem_base + X::O_COL, tmem_base, smem_u32(sV + st * TK::BYTES), j > 0);
         umma_commit(pv_done);
-        if (j + 1 < T_tiles) {  // S_{j+1} right behind P V_j (in-order pipe: P_j is read before it is overwritten)
-          const int sn = (j + 1) & 1;
-          mbar_wait(bar_kv + sn, ((j + 1) >> 1) & 1);
+      }
+      if (j + 1 < T_tiles) {  // S_{j+1} right behind P V_j (in-order pipe: P_j is read before it is overwritten)
+        const int sn = (j + 1) & 1;
+        mbar_wait(bar_kv + sn, ((j + 1) >> 1) & 1);
+        if constexpr (X::PAD_SUM) write_v_ones<DH>(sV + sn * TK::BYTES, lane);
+        if (lane == 0) {
           tc_fence_after();
           issue_qk<DH>(tmem_base, smem_u32(sQ), smem_u32(sK + sn * TK::BYTES));
           umma_commit(s_full);
         }
-        if (j + 2 < T_tiles) {
-          mbar_wait(pv_done, ph);  // K_j / V_j consumed: refill the stage with tile j + 2
+      }
+      if (j + 2 < T_tiles) {
+        mbar_wait(pv_done, ph);  // K_j / V_j consumed: refill the stage with tile j + 2
+        if (lane == 0) {
           mbar_arrive_expect_tx(bar_kv + st, 2 * TK::BYTES);
           tma_load_tile<DH, BN>(sK + st * TK::BYTES, &mk128, &mk32, bar_kv + st, (j + 2) * BN, h, b);
           tma_load_tile<DH, BN>(sV + st * TK::BYTES, &mv128, &mv32, bar_kv + st, (j + 2) * BN, h, b);
         }
       }
+      __syncwarp();
     }
   } else {
     // ================= softmax warps: thread = query row =================
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const float c = prm.scale_log2e;
-    float m_used = -INFINITY;
+    float m_used = -INFINITY, l_thr = 0.f;  // l_thr: thread-side row sum (unused when the V pad column carries it)
     for (int j = 0; j < T_tiles; ++j) {
       const uint32_t ph = j & 1;
       mbar_wait(s_full, ph);
@@ -221,7 +239,8 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
           const float m_new = grow ? mxc : m_used;
           const float alpha = ex2_approx(m_used - m_new);
           m_used = m_new;
-          mbar_wait(pv_done, ph ^ 1);  // O | L hold tiles 0..j-1
+          l_thr *= alpha;
+          mbar_wait(pv_done, ph ^ 1);  // O holds tiles 0..j-1
           tc_fence_after();
 #pragma unroll
           for (int cc = 0; cc < X::ACC_COLS / 16; ++cc) {
@@ -236,12 +255,15 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
       }
       // p = exp2(s*c - m_used), packed to fp16 pairs in place (s[0 .. BN/2) then hold the BN probabilities)
       const float negm = -m_used;
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int i = 0; i < BN; i += 2) {
         const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), c, negm));
         const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), c, negm));
+        if constexpr (!X::PAD_SUM) l0 += p0, l1 += p1;
         s[i >> 1] = pack_half2(p0, p1);
       }
+      if constexpr (!X::PAD_SUM) l_thr += l0 + l1;
 #pragma unroll
       for (int cc = 0; cc < BN / 64; ++cc) tmem_st32(lane_addr + cc * 32, s + cc * 32);  // P over the consumed S
       tmem_st_wait();
@@ -253,12 +275,12 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
     mbar_wait(pv_done, (T_tiles - 1) & 1);
     tc_fence_after();
     const int row = q0 + tid;
-    float l;
-    {
+    float l = l_thr;
+    if constexpr (X::PAD_SUM) {  // accumulator column DH = sum_j P_j * 1
       uint32_t r[16];
-      tmem_ld16(lane_addr + X::L_COL, r);
+      tmem_ld16(lane_addr + X::O_COL + (DH / 16) * 16, r);
       tmem_ld_wait();
-      l = __uint_as_float(r[0]);
+      l = __uint_as_float(r[DH % 16]);
     }
     const float inv = 1.f / l;
     __half* orow = prm.o + (int64_t)b * prm.o_sb + (int64_t)row * prm.o_sr + h * DH;

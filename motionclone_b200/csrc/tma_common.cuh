@@ -167,6 +167,25 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// one row (DHP fp16, DHP % 16 == 0) of a K-major SW128 tile part in shared memory -> DHP / 2 packed TMEM columns of the
+// calling thread's lane: how a resident [128][DH <= 48] operand tile becomes a tensor-memory A operand
+template <int DHP>
+__device__ __forceinline__ void smem_row_to_tmem(const uint8_t* part, int r, uint32_t taddr) {
+  static_assert(DHP % 16 == 0 && DHP <= 64, "one SW128 part");
+  uint32_t v[DHP / 2];
+#pragma unroll
+  for (int c = 0; c < DHP / 8; ++c) {
+    const uint4 x = *reinterpret_cast<const uint4*>(part + sw128_chunk_off(r, c));
+    v[4 * c] = x.x, v[4 * c + 1] = x.y, v[4 * c + 2] = x.z, v[4 * c + 3] = x.w;
+  }
+#pragma unroll
+  for (int c = 0; c < DHP / 16; ++c) tmem_st8(taddr + c * 8, v + c * 8);
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
