@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MC_ABI_VERSION 1
+#define MC_ABI_VERSION 2
 
 #define MC_OK 0
 #define MC_E_INVALID (-1)     /* bad argument (null pointer, unsupported shape, misaligned stride) */
@@ -184,10 +184,14 @@ int mc_groupnorm_nhwc(const void* x, const void* chan_bias, int frames_per_bias_
                       const void* beta, void* workspace, int64_t workspace_bytes, int N, int HW, int C, int G, float eps,
                       int fuse_silu, void* stream);
 /* LayerNorm over the last dim (models/attention.py:189,206,212; models/motion_module.py:204,210), C % 8 == 0, C <= 2048.
- * post_add (nullable): fp16 [frames, C] added after the norm to row r at frame (r / rows_per_frame) % frames — the
- * temporal positional encoding `x + pe[:, :f]` (models/motion_module.py:246, :281-282) on (b f)-major tokens. */
-int mc_layernorm(const void* x, void* y, const void* gamma, const void* beta, const void* post_add, int rows_per_frame,
-                 int frames, int64_t rows, int C, float eps, void* stream);
+ * post_add (nullable): fp16 [frames, C] added after the norm to row r at frame (r / rows_per_frame) % frames - the
+ * temporal positional encoding `x + pe[:, :f]` (models/motion_module.py:246, :281-282) on (b f)-major tokens.
+ * pre_bias (nullable): fp16 [C] added to x before the statistics (LayerNorm(x + pre_bias)). Used by the transformer
+ * blocks to carry the constant output biases of their projections inside the residual stream, so that every
+ * `residual + Linear(x)` of a block is ONE GEMM with beta = 1 instead of a GEMM and an elementwise pass
+ * (models/attention.py:271-300, models/motion_module.py:213-225). */
+int mc_layernorm(const void* x, void* y, const void* gamma, const void* beta, const void* post_add, const void* pre_bias,
+                 int rows_per_frame, int frames, int64_t rows, int C, float eps, void* stream);
 /* Backward of the three (input gradients only: weights are frozen on this path, t2v_video_sample.py:67-68).
  * mc_groupnorm_nhwc_stats copies the forward's finalised statistics out of its workspace: stats [N, G, 2] = (mean, rstd)
  * fp32, kept for the backward. mc_groupnorm_nhwc_bwd needs its own workspace (same size and zero-ticket rule). */
@@ -195,8 +199,8 @@ int mc_groupnorm_nhwc_stats(const void* workspace, void* stats, int N, int HW, i
 int mc_groupnorm_nhwc_bwd(const void* x, const void* chan_bias, int frames_per_bias_row, const void* dz, void* dx,
                           const void* stats, const void* gamma, const void* beta, void* workspace,
                           int64_t workspace_bytes, int N, int HW, int C, int G, int fuse_silu, void* stream);
-int mc_layernorm_bwd(const void* x, const void* dy, void* dx, const void* gamma, int64_t rows, int C, float eps,
-                     void* stream);
+int mc_layernorm_bwd(const void* x, const void* dy, void* dx, const void* gamma, const void* pre_bias, int64_t rows, int C,
+                     float eps, void* stream);
 int mc_geglu_bwd(const void* in, const void* dout, void* din, int64_t T, int I, void* stream);
 /* GEGLU of diffusers-0.16 FeedForward (models/attention.py:211, models/motion_module.py:209):
  * in [T, 2I] = [h | gate] -> out [T, I] = h * gelu_erf(gate), gelu output rounded to fp16 as in the eager graph */

@@ -64,7 +64,7 @@ def lib() -> ctypes.CDLL:
     L.mc_groupnorm_nhwc.restype = c_int
     L.mc_groupnorm_nhwc.argtypes = [P, P, c_int, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, c_int, P]
     L.mc_layernorm.restype = c_int
-    L.mc_layernorm.argtypes = [P, P, P, P, P, c_int, c_int, c_int64, c_int, c_float, P]
+    L.mc_layernorm.argtypes = [P, P, P, P, P, P, c_int, c_int, c_int64, c_int, c_float, P]
     L.mc_geglu.restype = c_int
     L.mc_geglu.argtypes = [P, P, c_int64, c_int, P]
     L.mc_groupnorm_nhwc_stats.restype = c_int
@@ -72,7 +72,7 @@ def lib() -> ctypes.CDLL:
     L.mc_groupnorm_nhwc_bwd.restype = c_int
     L.mc_groupnorm_nhwc_bwd.argtypes = [P, P, c_int, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, P]
     L.mc_layernorm_bwd.restype = c_int
-    L.mc_layernorm_bwd.argtypes = [P, P, P, P, c_int64, c_int, c_float, P]
+    L.mc_layernorm_bwd.argtypes = [P, P, P, P, P, c_int64, c_int, c_float, P]
     L.mc_geglu_bwd.restype = c_int
     L.mc_geglu_bwd.argtypes = [P, P, P, c_int64, c_int, P]
     L.mc_bias_residual_add.restype = c_int
@@ -87,8 +87,8 @@ def lib() -> ctypes.CDLL:
     L.mc_spatial_attn_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int]
     L.mc_spatial_attn_bwd.restype = c_int
     L.mc_spatial_attn_bwd.argtypes = [P] * 10 + [c_int, c_int, c_int, c_int] + [c_int64] * 12 + [c_float, P]
-    if L.mc_abi_version() != 1:
-        raise MotionCloneKernelError(f"ABI version mismatch: library {L.mc_abi_version()}, binding 1")
+    if L.mc_abi_version() != 2:
+        raise MotionCloneKernelError(f"ABI version mismatch: library {L.mc_abi_version()}, binding 2")
     _lib = L
     return L
 

@@ -23,7 +23,8 @@ union Vec8 {
 template <int VPL>  // vectors (of 8 halfs) per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                         const __half* __restrict__ gamma, const __half* __restrict__ beta,
-                                                        const __half* __restrict__ post_add, int rows_per_frame, int frames,
+                                                        const __half* __restrict__ post_add,
+                                                        const __half* __restrict__ pre_bias, int rows_per_frame, int frames,
                                                         int64_t rows, int C, float eps) {
   constexpr int R = 2;  // rows per warp and trip: both rows' loads are issued before either reduction starts
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -40,7 +41,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
       for (int i = 0; i < VPL; ++i) {
         const int v = lane + i * 32;
         a[r][i].u = make_uint4(0u, 0u, 0u, 0u);
-        if (live && v < V) a[r][i].u = *reinterpret_cast<const uint4*>(xr + v * 8);
+        if (live && v < V) {
+          a[r][i].u = *reinterpret_cast<const uint4*>(xr + v * 8);
+          if (pre_bias) {  // x + pre_bias[c] (fp16, as a separate elementwise add would round it) is what gets normalised
+            Vec8 pb;
+            pb.u = *reinterpret_cast<const uint4*>(pre_bias + v * 8);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[r][i].h2[j] = __hadd2(a[r][i].h2[j], pb.h2[j]);
+          }
+        }
       }
     }
 #pragma unroll
@@ -193,7 +202,8 @@ static bool g_gelu_lut_ready[64] = {};
 }  // namespace mc
 
 extern "C" int mc_layernorm(const void* x, void* y, const void* gamma, const void* beta, const void* post_add,
-                            int rows_per_frame, int frames, int64_t rows, int C, float eps, void* stream) {
+                            const void* pre_bias, int rows_per_frame, int frames, int64_t rows, int C, float eps,
+                            void* stream) {
   using namespace mc;
   if (!x || !y || !gamma || !beta || rows <= 0) {
     set_error("layernorm: null pointer or rows <= 0");
@@ -213,8 +223,8 @@ extern "C" int mc_layernorm(const void* x, void* y, const void* gamma, const voi
   const int vpl = (C / 8 + 31) / 32;
 #define MC_LN(V)                                                                                                \
   layernorm_kernel<V><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, (__half*)y, (const __half*)gamma,     \
-                                                        (const __half*)beta, (const __half*)post_add, rows_per_frame, \
-                                                        frames, rows, C, eps)
+                                                        (const __half*)beta, (const __half*)post_add,                 \
+                                                        (const __half*)pre_bias, rows_per_frame, frames, rows, C, eps)
   switch (vpl) {
     case 1: MC_LN(1); break;
     case 2: MC_LN(2); break;
@@ -276,7 +286,8 @@ namespace mc {
 template <int VPL>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __half* __restrict__ x, const __half* __restrict__ dy,
                                                             __half* __restrict__ dx, const __half* __restrict__ gamma,
-                                                            int64_t rows, int C, float eps) {
+                                                            const __half* __restrict__ pre_bias, int64_t rows, int C,
+                                                            float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int V = C / 8;
   for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
@@ -290,6 +301,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __half* __rest
       if (v < V) {
         a[i].u = *reinterpret_cast<const uint4*>(xr + v * 8);
         d[i].u = *reinterpret_cast<const uint4*>(dr + v * 8);
+        if (pre_bias) {
+          Vec8 pb;
+          pb.u = *reinterpret_cast<const uint4*>(pre_bias + v * 8);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[i].h2[j] = __hadd2(a[i].h2[j], pb.h2[j]);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += __half2float(a[i].h[j]);
       }
@@ -382,8 +399,8 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __half* __restrict
 
 }  // namespace mc
 
-extern "C" int mc_layernorm_bwd(const void* x, const void* dy, void* dx, const void* gamma, int64_t rows, int C, float eps,
-                                void* stream) {
+extern "C" int mc_layernorm_bwd(const void* x, const void* dy, void* dx, const void* gamma, const void* pre_bias,
+                                int64_t rows, int C, float eps, void* stream) {
   using namespace mc;
   if (!x || !dy || !dx || !gamma || rows <= 0) {
     set_error("layernorm_bwd: null pointer or rows <= 0");
@@ -399,7 +416,7 @@ extern "C" int mc_layernorm_bwd(const void* x, const void* dy, void* dx, const v
   const int vpl = (C / 8 + 31) / 32;
 #define MC_LNB(V)                                                                                                     \
   layernorm_bwd_kernel<V><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, (const __half*)dy, (__half*)dx,         \
-                                                            (const __half*)gamma, rows, C, eps)
+                                                            (const __half*)gamma, (const __half*)pre_bias, rows, C, eps)
   switch (vpl) {
     case 1: MC_LNB(1); break;
     case 2: MC_LNB(2); break;

@@ -405,45 +405,47 @@ class GroupNormNHWCFn(torch.autograd.Function):
 
 
 def layernorm(x: Tensor, weight: Tensor, bias: Tensor, eps: float, post_add: Optional[Tensor] = None,
-              rows_per_frame: int = 0) -> Tensor:
-    """LayerNorm over the last dim; `post_add` [F, C] is added to row r at frame (r // rows_per_frame) % F (the temporal
-    positional encoding on (b f)-major tokens)."""
+              rows_per_frame: int = 0, pre_bias: Optional[Tensor] = None) -> Tensor:
+    """LayerNorm over the last dim of (x + pre_bias); `post_add` [F, C] is added to row r at frame
+    (r // rows_per_frame) % F (the temporal positional encoding on (b f)-major tokens)."""
     _require(x, "x")
     x = x.contiguous()
     C = x.shape[-1]
     weight, bias = _require_param(weight, "layernorm weight", x, C), _require_param(bias, "layernorm bias", x, C)
+    if pre_bias is not None:
+        pre_bias = _require_param(pre_bias, "layernorm pre_bias", x, C)
     y = torch.empty_like(x)
     frames = 0
     if post_add is not None:
         _require(post_add, "post_add")
         post_add = post_add.contiguous()
         frames = post_add.shape[0]
-    st = _lib.lib().mc_layernorm(_ptr(x), _ptr(y), _ptr(weight), _ptr(bias), _ptr(post_add), int(rows_per_frame), frames,
-                                 x.numel() // C, C, float(eps), _stream())
+    st = _lib.lib().mc_layernorm(_ptr(x), _ptr(y), _ptr(weight), _ptr(bias), _ptr(post_add), _ptr(pre_bias),
+                                 int(rows_per_frame), frames, x.numel() // C, C, float(eps), _stream())
     _lib.check(st, "mc_layernorm")
     return y
 
 
 class LayerNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, eps: float, post_add, rows_per_frame: int):
+    def forward(ctx, x, weight, bias, eps: float, post_add, rows_per_frame: int, pre_bias=None):
         x = x.contiguous()
-        ctx.save_for_backward(x, weight)
+        ctx.save_for_backward(x, weight, pre_bias)
         ctx.eps = eps
-        return layernorm(x, weight, bias, eps, post_add, rows_per_frame)
+        return layernorm(x, weight, bias, eps, post_add, rows_per_frame, pre_bias)
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, weight, pre_bias = ctx.saved_tensors
         _require(dy, "dy")
         dy = dy.contiguous()
         C = x.shape[-1]
         weight = _require_param(weight, "layernorm weight", x, C)
         dx = torch.empty_like(x)
-        st = _lib.lib().mc_layernorm_bwd(_ptr(x), _ptr(dy), _ptr(dx), _ptr(weight), x.numel() // C, C, float(ctx.eps),
-                                         _stream())
+        st = _lib.lib().mc_layernorm_bwd(_ptr(x), _ptr(dy), _ptr(dx), _ptr(weight), _ptr(pre_bias), x.numel() // C, C,
+                                         float(ctx.eps), _stream())
         _lib.check(st, "mc_layernorm_bwd")
-        return dx, None, None, None, None, None
+        return dx, None, None, None, None, None, None
 
 
 def geglu(x: Tensor) -> Tensor:

@@ -44,15 +44,40 @@ class LayerNorm(nn.LayerNorm):
     """nn.LayerNorm (same parameters / state-dict keys) on csrc/norm_act.cu's warp-per-row kernels (forward, and the
     input gradient when the guided pass runs under autograd with frozen weights)."""
 
-    def forward(self, x, post_add=None, rows_per_frame: int = 0):
-        """post_add [F, C]: added after the norm to the rows of frame (r // rows_per_frame) % F (temporal PE)."""
+    def forward(self, x, post_add=None, rows_per_frame: int = 0, pre_bias=None):
+        """post_add [F, C]: added after the norm to the rows of frame (r // rows_per_frame) % F (temporal PE).
+        pre_bias [C]: LayerNorm(x + pre_bias) - see `fold_residual_biases`."""
         c = x.shape[-1]
         _need_kernels(x, "LayerNorm")
         if not (self.elementwise_affine and c % 8 == 0 and c <= 1280 and _frozen(self.weight, self.bias)):
             raise NotImplementedError("LayerNorm kernel: affine, frozen weights, C % 8 == 0, C <= 1280")
         if torch.is_grad_enabled() and x.requires_grad:
-            return ops.LayerNormFn.apply(x, self.weight, self.bias, self.eps, post_add, rows_per_frame)
-        return ops.layernorm(x, self.weight, self.bias, self.eps, post_add, rows_per_frame)
+            return ops.LayerNormFn.apply(x, self.weight, self.bias, self.eps, post_add, rows_per_frame, pre_bias)
+        return ops.layernorm(x, self.weight, self.bias, self.eps, post_add, rows_per_frame, pre_bias)
+
+
+def linear_into_residual(x, linear: nn.Linear, residual):
+    """residual + x @ W^T as ONE GEMM (beta = 1 epilogue) - the projection's bias is NOT added here: the caller carries it
+    inside the residual stream (fold_residual_biases)."""
+    c_out = linear.out_features
+    return torch.addmm(residual.reshape(-1, c_out), x.reshape(-1, x.shape[-1]), linear.weight.t()).view(residual.shape)
+
+
+def fold_residual_biases(biases):
+    """A transformer block computes  t1 = t + f1(t) + b1,  t2 = t1 + f2(t1) + b2,  t3 = t2 + f3(t2) + b3  (b_i: the output
+    biases of its projections; attention.py:271-300, motion_module.py:213-225). With the stream shifted by the constant
+    B = b1 + b2 + b3 up front (folded into the bias of the proj_in GEMM that produces t) every residual add becomes the
+    beta = 1 epilogue of its GEMM:  t' = t + B;  t1' = t' + f1(LN(t' - B));  t2' = t1' + f2(LN(t1' - b2 - b3));
+    t3 = t2' + f3(LN(t2' - b3))  - identical algebra, three elementwise passes fewer. Returns (B, [-B, -(b2+b3), -b3])
+    as fp16 tensors: the shift and the `pre_bias` of the three LayerNorms."""
+    zero = torch.zeros_like(biases[0])
+    bs = [b if b is not None else zero for b in biases]
+    suffix = [None] * len(bs)
+    acc = zero
+    for i in range(len(bs) - 1, -1, -1):
+        acc = acc + bs[i]
+        suffix[i] = acc
+    return suffix[0].contiguous(), [(-sfx).contiguous() for sfx in suffix]
 
 
 class GroupNormNHWC(nn.GroupNorm):
@@ -99,10 +124,13 @@ class FeedForward(nn.Module):
         inner = int(dim * mult)
         self.net = nn.ModuleList([GEGLU(dim, inner), nn.Dropout(dropout), nn.Linear(inner, dim_out or dim)])
 
-    def forward(self, x):
-        for m in self.net:
-            x = m(x)
-        return x
+    def forward(self, x, residual=None):
+        """residual given: returns residual + net(x) WITHOUT net[2]'s bias (carried by the caller, fold_residual_biases)."""
+        if residual is None:
+            for m in self.net:
+                x = m(x)
+            return x
+        return linear_into_residual(self.net[0](x), self.net[2], residual)
 
 
 class CrossAttention(nn.Module):
@@ -218,9 +246,11 @@ class CrossAttention(nn.Module):
             return ops.CrossAttentionTC.apply(q, k, v, h, self.scale)
         return ops.cross_attention_forward(q, k, v, h, self.scale)
 
-    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, text_batch: Optional[int] = None):
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, text_batch: Optional[int] = None,
+                residual=None):
         """hidden_states `[(b f), N, C]`. encoder_hidden_states: `[(b f), n, c]` as in the reference, or `[b, n, c]`
-        with `text_batch=b` so the text K/V are projected once per prompt."""
+        with `text_batch=b` so the text K/V are projected once per prompt. `residual` given: returns
+        residual + to_out(attention) WITHOUT to_out's bias, as one GEMM (fold_residual_biases)."""
         if attention_mask is not None:
             raise NotImplementedError("no mask reaches attention on the live path (SURVEY appendix)")
         _need_kernels(hidden_states, "CrossAttention")
@@ -257,6 +287,8 @@ class CrossAttention(nn.Module):
             else:
                 o = ops.cross_attention_forward(q, k, v, h, self.scale)
             o = o.view(bf, n, inner)
+        if residual is not None:
+            return linear_into_residual(o, self.to_out[0], residual)
         return self.to_out[1](self.to_out[0](o))
 
 
@@ -294,7 +326,22 @@ class BasicTransformerBlock(nn.Module):
         if self.attn2 is not None:
             self.attn2._use_memory_efficient_attention_xformers = use
 
-    def forward(self, hidden_states, encoder_hidden_states=None, timestep=None, attention_mask=None, video_length=None):
+    def residual_biases(self):
+        """Output biases of the three residual branches, in order (attention.py:271-300)."""
+        return [self.attn1.to_out[0].bias, self.attn2.to_out[0].bias if self.attn2 is not None else None,
+                self.ff.net[2].bias]
+
+    def forward(self, hidden_states, encoder_hidden_states=None, timestep=None, attention_mask=None, video_length=None,
+                folded=None):
+        """`folded` = the pre-bias list of fold_residual_biases: `hidden_states` then is the stream shifted by the sum of
+        this block's output biases and the result is the TRUE block output (see fold_residual_biases)."""
+        if folded is not None:
+            h = self.attn1(self.norm1(hidden_states, pre_bias=folded[0]), attention_mask=attention_mask,
+                           residual=hidden_states)
+            if self.attn2 is not None:
+                h = self.attn2(self.norm2(h, pre_bias=folded[1]), encoder_hidden_states=encoder_hidden_states,
+                               attention_mask=attention_mask, residual=h)
+            return self.ff(self.norm3(h, pre_bias=folded[2]), residual=h)
         hidden_states = self.attn1(self.norm1(hidden_states), attention_mask=attention_mask) + hidden_states
         if self.attn2 is not None:
             hidden_states = self.attn2(self.norm2(hidden_states), encoder_hidden_states=encoder_hidden_states,
@@ -338,6 +385,17 @@ class Transformer3DModel(nn.Module):
                                   unet_use_temporal_attention=unet_use_temporal_attention)
             for _ in range(num_layers)])
 
+    def _folded(self):
+        """(proj_in bias + sum of the block's output biases, pre-biases of its three LayerNorms); rebuilt when a bias
+        tensor was replaced, moved or cast (weights are frozen on this path)."""
+        bs = [self.proj_in.bias] + [b for b in self.transformer_blocks[0].residual_biases() if b is not None]
+        key = tuple((b.data_ptr(), b._version, b.dtype, b.device) for b in bs)
+        if getattr(self, "_fold_cache", None) is None or self._fold_cache[0] != key:
+            with torch.no_grad():
+                shift, pre = fold_residual_biases([b.detach() for b in self.transformer_blocks[0].residual_biases()])
+                self._fold_cache = (key, ((self.proj_in.bias.detach() + shift).contiguous(), pre))
+        return self._fold_cache[1]
+
     @staticmethod
     def _as_linear(conv_or_linear, t):
         w = conv_or_linear.weight
@@ -353,10 +411,19 @@ class Transformer3DModel(nn.Module):
         n, c, h, w = hidden_states.shape
         residual = hidden_states.permute(0, 2, 3, 1).reshape(n, h * w, c)  # token view (zero-copy when channels_last)
         t = self.norm(hidden_states).permute(0, 2, 3, 1).reshape(n, h * w, c)
-        t = self._as_linear(self.proj_in, t)
-        for block in self.transformer_blocks:
-            # encoder_hidden_states stays [b, 77, c]: K/V are projected once per prompt, not per frame
-            t = block(t, encoder_hidden_states=encoder_hidden_states, timestep=timestep, video_length=video_length)
+        if len(self.transformer_blocks) == 1 and self.proj_in.bias is not None:
+            # the block's three residual adds ride in their GEMMs' epilogues: its output biases are pre-added to the stream
+            # through proj_in's bias and taken back out inside the LayerNorms (fold_residual_biases)
+            shift, pre = self._folded()
+            w = self.proj_in.weight
+            t = F.linear(t, w.reshape(w.shape[0], w.shape[1]), shift)
+            t = self.transformer_blocks[0](t, encoder_hidden_states=encoder_hidden_states, timestep=timestep,
+                                           video_length=video_length, folded=pre)
+        else:
+            t = self._as_linear(self.proj_in, t)
+            for block in self.transformer_blocks:
+                # encoder_hidden_states stays [b, 77, c]: K/V are projected once per prompt, not per frame
+                t = block(t, encoder_hidden_states=encoder_hidden_states, timestep=timestep, video_length=video_length)
         t = self._as_linear(self.proj_out, t) + residual  # contiguous + contiguous: vectorised add
         out = t.reshape(n, h, w, -1).permute(0, 3, 1, 2)
         if five_d:

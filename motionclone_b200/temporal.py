@@ -22,7 +22,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .spatial import CrossAttention, FeedForward, GroupNormNHWC, LayerNorm
+from .spatial import (CrossAttention, FeedForward, GroupNormNHWC, LayerNorm, fold_residual_biases,
+                      linear_into_residual)
 
 
 def zero_module(module: nn.Module) -> nn.Module:
@@ -115,7 +116,7 @@ class VersatileAttention(CrossAttention):
         return f"(Module Info) Attention_Mode: {self.attention_mode}, Is_Cross_Attention: {self.is_cross_attention}"
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, video_length=None,
-                pe_applied: bool = False):
+                pe_applied: bool = False, residual=None):
         if self.attention_mode != "Temporal" or encoder_hidden_states is not None or self.added_kv_proj_dim is not None:
             raise NotImplementedError  # as motion_module.py:286, :298 (cross-frame text attention is never configured)
         if attention_mask is not None or self.group_norm is not None:
@@ -149,6 +150,8 @@ class VersatileAttention(CrossAttention):
             proc.top1 = top1
             proc.gathered = gathered if mode == "gather" else None
 
+        if residual is not None:  # residual + to_out(o) without its bias, as one GEMM (spatial.fold_residual_biases)
+            return linear_into_residual(o.view(bf, d, c), self.to_out[0], residual)
         o = self.to_out[1](self.to_out[0](o))  # :337-340
         return o.view(bf, d, c)
 
@@ -177,14 +180,27 @@ class TemporalTransformerBlock(nn.Module):
         self.ff = FeedForward(dim, dropout=dropout, activation_fn=activation_fn)
         self.ff_norm = LayerNorm(dim)
 
-    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, video_length=None):
+    def residual_biases(self):
+        """Output biases of the residual branches in order (motion_module.py:213-225)."""
+        return [a.to_out[0].bias for a in self.attention_blocks] + [self.ff.net[2].bias]
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, video_length=None, folded=None):
+        """`folded`: pre-bias list of spatial.fold_residual_biases (the stream arrives shifted by the block's output biases
+        and every residual add is the beta = 1 epilogue of its GEMM); the TRUE block output is returned."""
         d = hidden_states.shape[1]
-        for attn, norm in zip(self.attention_blocks, self.norms):
+        for i, (attn, norm) in enumerate(zip(self.attention_blocks, self.norms)):
             # LayerNorm (:215) and the positional-encoding add (:281-282) in one pass over the tokens
             pe = attn.pos_encoder.pe[0, :video_length].to(hidden_states.dtype) if attn.pos_encoder is not None else None
-            hidden_states = attn(norm(hidden_states, post_add=pe, rows_per_frame=d),
-                                 encoder_hidden_states=encoder_hidden_states if attn.is_cross_attention else None,
-                                 video_length=video_length, pe_applied=True) + hidden_states
+            ctx = encoder_hidden_states if attn.is_cross_attention else None
+            if folded is not None:
+                hidden_states = attn(norm(hidden_states, post_add=pe, rows_per_frame=d, pre_bias=folded[i]),
+                                     encoder_hidden_states=ctx, video_length=video_length, pe_applied=True,
+                                     residual=hidden_states)
+            else:
+                hidden_states = attn(norm(hidden_states, post_add=pe, rows_per_frame=d), encoder_hidden_states=ctx,
+                                     video_length=video_length, pe_applied=True) + hidden_states
+        if folded is not None:
+            return self.ff(self.ff_norm(hidden_states, pre_bias=folded[-1]), residual=hidden_states)
         return self.ff(self.ff_norm(hidden_states)) + hidden_states
 
 
@@ -213,6 +229,15 @@ class TemporalTransformer3DModel(nn.Module):
             for _ in range(num_layers)])
         self.proj_out = nn.Linear(inner_dim, in_channels)
 
+    def _folded(self):
+        bs = [self.proj_in.bias] + [b for b in self.transformer_blocks[0].residual_biases() if b is not None]
+        key = tuple((b.data_ptr(), b._version, b.dtype, b.device) for b in bs)
+        if getattr(self, "_fold_cache", None) is None or self._fold_cache[0] != key:
+            with torch.no_grad():
+                shift, pre = fold_residual_biases([b.detach() for b in self.transformer_blocks[0].residual_biases()])
+                self._fold_cache = (key, ((self.proj_in.bias.detach() + shift).contiguous(), pre))
+        return self._fold_cache[1]
+
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, video_length=None):
         five_d = hidden_states.dim() == 5
         if five_d:
@@ -224,9 +249,15 @@ class TemporalTransformer3DModel(nn.Module):
         residual = hidden_states.permute(0, 2, 3, 1).reshape(n, h * w, c)  # token view (zero-copy when channels_last)
         t = self.norm(hidden_states)
         t = t.permute(0, 2, 3, 1).reshape(n, h * w, c)  # a view when the activation is channels_last
-        t = self.proj_in(t)
-        for block in self.transformer_blocks:
-            t = block(t, encoder_hidden_states=encoder_hidden_states, video_length=video_length)
+        if len(self.transformer_blocks) == 1 and self.proj_in.bias is not None:
+            shift, pre = self._folded()
+            t = F.linear(t, self.proj_in.weight, shift)
+            t = self.transformer_blocks[0](t, encoder_hidden_states=encoder_hidden_states, video_length=video_length,
+                                           folded=pre)
+        else:
+            t = self.proj_in(t)
+            for block in self.transformer_blocks:
+                t = block(t, encoder_hidden_states=encoder_hidden_states, video_length=video_length)
         t = self.proj_out(t) + residual
         out = t.reshape(n, h, w, c).permute(0, 3, 1, 2)
         if five_d:

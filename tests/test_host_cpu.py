@@ -28,7 +28,7 @@ def test_library_exports_every_header_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/motionclone_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == declared
-    assert lib.mc_abi_version() == 1
+    assert lib.mc_abi_version() == 2
 
 
 def test_ops_refuse_cpu_tensors():
