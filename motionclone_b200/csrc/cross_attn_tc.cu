@@ -1,4 +1,5 @@
-// Text cross-attention forward on 5th-gen tensor cores (tcgen05) with TMEM accumulators, sm_100a.
+// Text cross-attention BACKWARD (dQ) on 5th-gen tensor cores (tcgen05) with TMEM accumulators, sm_100a. The forward is
+// csrc/cross_attn_fwd_tc.cu; the shared pieces (softmax_row_tmem, XACfg) below serve the backward's recompute.
 //
 // Replaces the xformers seam for `attn2` (reference models/attention.py:193-201, :280-285 -> :535-542,
 // xformers.ops.memory_efficient_attention): O = softmax(scale * Q K^T) V with Q [b, f*N, C] (all frames of one prompt:
@@ -75,116 +76,6 @@ struct XACfg {
   static constexpr int TCOLS_BWD = 256;
   static constexpr int SMEM_BWD = 128 + 2 * Q_BYTES + 2 * KV_BYTES + P_BYTES;
 };
-
-template <int DH>
-__global__ void __launch_bounds__(kXThreads) cross_attn_fwd_tc_kernel(const XAParams prm) {
-  using X = XACfg<DH>;
-  constexpr int DHP = X::DHP, KCQ = X::KCQ;
-
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);          // MMA-done barrier
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
-  uint8_t* sQ = smem + 128;                                   // K-major [KCQ][128][16 B]
-  uint8_t* sK = sQ + X::Q_BYTES;                              // K-major [KCQ][80][16 B]
-  uint8_t* sV = sK + X::KV_BYTES;                             // MN-major [KCQ][80][16 B] (n-chunk c, key j)
-  uint8_t* sP = sV + X::KV_BYTES;                             // K-major [10][128][16 B]
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int h = blockIdx.x, qt = blockIdx.y, b = blockIdx.z;  // heads fastest: the 8 CTAs sharing Q rows run together
-  const int q0 = qt * kXM;
-
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(X::TCOLS_FWD)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-
-  stage_chunks<DH, KCQ, kXM, kXM, kXThreads>(sQ, prm.q + (int64_t)b * prm.q_sb + h * DH, prm.q_sr, q0, prm.Nq, tid);
-  stage_chunks<DH, KCQ, kXN, kXN, kXThreads>(sK, prm.k + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, tid);
-  stage_chunks<DH, KCQ, kXN, kXN, kXThreads>(sV, prm.v + (int64_t)b * prm.kv_sb + h * DH, prm.kv_sr, 0, prm.Nk, tid);
-  fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // ---- S = Q K^T ----
-  if (tid == 0) {
-    const uint32_t idesc = umma_instr_desc_f16(kXM, kXN, false);
-#pragma unroll
-    for (int ks = 0; ks < X::KS1; ++ks) {
-      const uint64_t a = umma_smem_desc(smem_u32(sQ) + ks * 2 * kXM * 16, kXM * 16, 128);
-      const uint64_t bd = umma_smem_desc(smem_u32(sK) + ks * 2 * kXN * 16, kXN * 16, 128);
-      umma_f16(tmem_base, a, bd, idesc, ks > 0 ? 1u : 0u);
-    }
-    umma_commit(bar);
-  }
-  mbar_wait(bar, 0);
-  tc_fence_after();
-
-  // ---- softmax over the valid keys of row `tid` (TMEM lane tid), P -> fp16 -> sP (K-major chunks) ----
-  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-  {
-    uint32_t ph[kXN / 2];
-    softmax_row_tmem(lane_addr, prm.Nk, prm.scale, ph);
-#pragma unroll
-    for (int c = 0; c < kXN / 8; ++c)
-      *reinterpret_cast<uint4*>(sP + (c * kXM + tid) * 16) = make_uint4(ph[4 * c], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();  // every thread's tcgen05.ld of S has completed: its columns may be overwritten by O
-  tc_fence_after();
-
-  // ---- O = P V  (A = P K-major; B = V MN-major: n-chunks SBO apart, 8-key groups LBO = 128 B apart) ----
-  if (tid == 0) {
-    const uint32_t idesc = umma_instr_desc_f16(kXM, DHP, true);
-#pragma unroll
-    for (int ks = 0; ks < X::KS2; ++ks) {
-      const uint64_t a = umma_smem_desc(smem_u32(sP) + ks * 2 * kXM * 16, kXM * 16, 128);
-      const uint64_t bd = umma_smem_desc(smem_u32(sV) + ks * 2 * 128, 128, kXN * 16);
-      umma_f16(tmem_base, a, bd, idesc, ks > 0 ? 1u : 0u);
-    }
-    umma_commit(bar);
-  }
-  mbar_wait(bar, 1);
-  tc_fence_after();
-
-  // ---- epilogue: O row `tid` from TMEM -> fp16 -> global ----
-  {
-    const int row = q0 + tid;
-    __half* orow = prm.o + (int64_t)b * prm.o_sb + (int64_t)row * prm.o_sr + h * DH;
-#pragma unroll
-    for (int c = 0; c < DHP / 16; ++c) {
-      uint32_t r[16];
-      tmem_ld16(lane_addr + c * 16, r);
-      tmem_ld_wait();
-      if (row < prm.Nq) {
-#pragma unroll
-        for (int half8 = 0; half8 < 2; ++half8) {
-          if (c * 16 + half8 * 8 < DH) {
-            uint4 pk;
-            pk.x = pack_half2(__uint_as_float(r[half8 * 8 + 0]), __uint_as_float(r[half8 * 8 + 1]));
-            pk.y = pack_half2(__uint_as_float(r[half8 * 8 + 2]), __uint_as_float(r[half8 * 8 + 3]));
-            pk.z = pack_half2(__uint_as_float(r[half8 * 8 + 4]), __uint_as_float(r[half8 * 8 + 5]));
-            pk.w = pack_half2(__uint_as_float(r[half8 * 8 + 6]), __uint_as_float(r[half8 * 8 + 7]));
-            *reinterpret_cast<uint4*>(orow + c * 16 + half8 * 8) = pk;
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(X::TCOLS_FWD) : "memory");
-  }
-}
 
 // ================================================================================================================
 // backward with respect to Q only: the text K / V come from frozen projections of a constant prompt embedding
@@ -339,17 +230,6 @@ __global__ void __launch_bounds__(kXThreads) cross_attn_bwd_dq_tc_kernel(const X
 }
 
 template <int DH>
-static int launch_xattn(const XAParams& prm, cudaStream_t st) {
-  const int smem = XACfg<DH>::SMEM_FWD;
-  auto kern = cross_attn_fwd_tc_kernel<DH>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  dim3 grid(prm.H, (prm.Nq + kXM - 1) / kXM, prm.B);
-  kern<<<grid, kXThreads, smem, st>>>(prm);
-  count_launch();
-  return check_launch("cross_attn_fwd_tc");
-}
-
-template <int DH>
 static int launch_xattn_bwd(const XAParams& prm, cudaStream_t st) {
   const int smem = XACfg<DH>::SMEM_BWD;
   auto kern = cross_attn_bwd_dq_tc_kernel<DH>;
@@ -394,24 +274,6 @@ static int xattn_check(const char* what, const void* q, const void* k, const voi
     case 160: return FN<160>(prm, st);              \
     default: break;                                 \
   }
-
-extern "C" int mc_cross_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int Nq, int Nk, int H, int DH,
-                                 int64_t q_stride_b, int64_t q_stride_row, int64_t kv_stride_b, int64_t kv_stride_row,
-                                 int64_t o_stride_b, int64_t o_stride_row, float scale, void* stream) {
-  using namespace mc;
-  const int rc = xattn_check("cross_attn_fwd", q, k, v, o, B, Nq, Nk, H,
-                             q_stride_row | kv_stride_row | o_stride_row | q_stride_b | kv_stride_b | o_stride_b);
-  if (rc != MC_OK) return rc;
-  XAParams prm{};
-  prm.q = (const __half*)q, prm.k = (const __half*)k, prm.v = (const __half*)v, prm.o = (__half*)o;
-  prm.q_sb = q_stride_b, prm.q_sr = q_stride_row, prm.kv_sb = kv_stride_b, prm.kv_sr = kv_stride_row;
-  prm.o_sb = o_stride_b, prm.o_sr = o_stride_row;
-  prm.B = B, prm.Nq = Nq, prm.Nk = Nk, prm.H = H, prm.scale = scale;
-  cudaStream_t st = (cudaStream_t)stream;
-  MC_XATTN_DISPATCH(launch_xattn)
-  set_error("cross_attn_fwd: unsupported head dim %d (8, 16, 32, 40, 64, 80, 160)", DH);
-  return MC_E_UNSUPPORTED;
-}
 
 extern "C" int mc_cross_attn_bwd_dq(const void* q, const void* k, const void* v, const void* d_o, void* dq, int B, int Nq,
                                     int Nk, int H, int DH, int64_t q_stride_b, int64_t q_stride_row, int64_t kv_stride_b,
