@@ -415,8 +415,8 @@ class Transformer3DModel(nn.Module):
             # the block's three residual adds ride in their GEMMs' epilogues: its output biases are pre-added to the stream
             # through proj_in's bias and taken back out inside the LayerNorms (fold_residual_biases)
             shift, pre = self._folded()
-            w = self.proj_in.weight
-            t = F.linear(t, w.reshape(w.shape[0], w.shape[1]), shift)
+            w_in = self.proj_in.weight
+            t = F.linear(t, w_in.reshape(w_in.shape[0], w_in.shape[1]), shift)
             t = self.transformer_blocks[0](t, encoder_hidden_states=encoder_hidden_states, timestep=timestep,
                                            video_length=video_length, folded=pre)
         else:
