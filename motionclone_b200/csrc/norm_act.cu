@@ -252,9 +252,8 @@ extern "C" int mc_geglu(const void* in, void* out, int64_t T, int I, void* strea
   }
   const int64_t nvec = T * (I / 8);
   cudaStream_t st = (cudaStream_t)stream;
-  static const int env_nolut = getenv("MC_GEGLU_NO_LUT") ? atoi(getenv("MC_GEGLU_NO_LUT")) : 0;  // A/B knob
   int dev = 0, sms = 148;
-  if (!env_nolut && nvec >= (int64_t)1 << 20 && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+  if (nvec >= (int64_t)1 << 20 && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
     // >= 16 MB of output: the persistent table kernel (one 1024-thread CTA per SM, 128 KB of shared memory)
     if (!g_gelu_lut_ready[dev]) {  // once per device, ordered before the first use on this stream
       gelu_lut_init_kernel<<<65536 / 256, 256, 0, st>>>();

@@ -463,115 +463,6 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_fwd_kernel(const TAPara
 }
 
 // ================================================================================================================
-// forward, persistent + pipelined: one CTA per SM slot loops over tiles. Warp 0 is the producer (bulk loads of tile
-// i+1.. into a ring of NSTAGE shared-memory stages, bulk stores of finished O tiles), warps 1..NCW consume.
-//   full[s]  : producer arrive.expect_tx + TMA complete_tx  -> consumers
-//   empty[s] : one arrive per consumer warp (after its O rows are in shared memory) -> producer
-// Loads of the next tiles are in flight while the current one is computed, and there is no wave quantisation: the
-// non-persistent kernel above loses both at the small layers (profiles/README.md).
-// ================================================================================================================
-template <int DH, int L, int NCW, int NSTAGE>
-__global__ void __launch_bounds__((NCW + 1) * 32) temporal_attn_fwd_persistent_kernel(const TAParams prm, int n_tiles) {
-  using C = TACfg<DH, L>;
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* empty = full + NSTAGE;
-  const TileGeom g = prm.g;
-  const int stage_bytes = (g.fused ? 1 : 3) * g.tensor_bytes;
-  uint8_t* stage0 = smem + kHeaderBytes;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_hg = prm.H / g.HG, n_pt = prm.D / g.P;
-  const bool has_o = prm.o != nullptr;
-  const uint32_t tbytes = (uint32_t)L * g.P * g.W * 2;
-
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(full + s, 1);
-      mbar_init(empty + s, NCW);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  auto coords = [&](int tile, int& b, int& p0, int& h0) {
-    const int hg = tile % n_hg;
-    const int t2 = tile / n_hg;
-    b = t2 / n_pt;
-    p0 = (t2 % n_pt) * g.P;
-    h0 = hg * g.HG;
-  };
-
-  if (warp == 0) {
-    // ------------------------------------------------ producer ------------------------------------------------
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int s = it % NSTAGE, r = it / NSTAGE;
-      uint8_t* sQ = stage0 + s * stage_bytes;
-      int b, p0, h0;
-      if (r > 0) {  // the tile that used this stage NSTAGE iterations ago: wait for its consumers, send its O home
-        mbar_wait(empty + s, (r - 1) & 1);
-        if (has_o) {
-          coords(tile - NSTAGE * (int)gridDim.x, b, p0, h0);
-          const int64_t obase = (int64_t)b * prm.out.stride_b + (int64_t)p0 * prm.out.stride_p + h0 * DH;
-          store_rows<L>(prm.o, sQ, g.pitch, g.PS, g.W, g.P, prm.out, obase, lane);
-          bulk_commit();
-          bulk_wait_read_all();  // the stage may be overwritten once the store engine has read it
-        }
-        __syncwarp();
-      }
-      coords(tile, b, p0, h0);
-      const int64_t gbase = (int64_t)b * prm.in.stride_b + (int64_t)p0 * prm.in.stride_p + h0 * DH;
-      if (g.fused) {
-        if (lane == 0) mbar_arrive_expect_tx(full + s, 3 * tbytes);
-        __syncwarp();
-        stage_rows<L>(sQ, g.pitch, g.PS, 3 * g.W, g.P, prm.q, prm.in, gbase, full + s, lane);
-      } else {
-        if (lane == 0) mbar_arrive_expect_tx(full + s, (has_o ? 3 : 2) * tbytes);
-        __syncwarp();
-        stage_rows<L>(sQ, g.pitch, g.PS, g.W, g.P, prm.q, prm.in, gbase, full + s, lane);
-        stage_rows<L>(sQ + g.tensor_bytes, g.pitch, g.PS, g.W, g.P, prm.k, prm.in, gbase, full + s, lane);
-        if (has_o) stage_rows<L>(sQ + 2 * g.tensor_bytes, g.pitch, g.PS, g.W, g.P, prm.v, prm.in, gbase, full + s, lane);
-      }
-    }
-    // drain: O of the last (up to NSTAGE) tiles
-    const int n_it = it;
-    for (int j = (n_it > NSTAGE ? n_it - NSTAGE : 0); j < n_it; ++j) {
-      const int s = j % NSTAGE, r = j / NSTAGE;
-      mbar_wait(empty + s, r & 1);
-      if (has_o) {
-        int b, p0, h0;
-        coords(blockIdx.x + j * (int)gridDim.x, b, p0, h0);
-        const int64_t obase = (int64_t)b * prm.out.stride_b + (int64_t)p0 * prm.out.stride_p + h0 * DH;
-        store_rows<L>(prm.o, stage0 + s * stage_bytes, g.pitch, g.PS, g.W, g.P, prm.out, obase, lane);
-        bulk_commit();
-      }
-    }
-    bulk_wait_read_all();
-  } else {
-    // ------------------------------------------------ consumers -----------------------------------------------
-    const int cw = warp - 1;
-    const int n_items = ((g.P + C::PP - 1) / C::PP) * g.HG;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int s = it % NSTAGE, r = it / NSTAGE;
-      uint8_t* sQ = stage0 + s * stage_bytes;
-      uint8_t* sK = g.fused ? sQ + g.W * 2 : sQ + g.tensor_bytes;
-      uint8_t* sV = g.fused ? sQ + g.W * 4 : sQ + 2 * g.tensor_bytes;
-      int b, p0, h0;
-      coords(tile, b, p0, h0);
-      mbar_wait(full + s, r & 1);
-      bool v_ready = true;
-      for (int item = cw; item < n_items; item += NCW)
-        fwd_item<C>(prm, g, sQ, smem_u32(sQ), smem_u32(sK), smem_u32(sV), b, p0, h0, item, lane, has_o, nullptr, v_ready);
-      if (has_o) fence_proxy_async();  // O rows (generic-proxy writes) -> visible to the bulk-store engine
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty + s);
-    }
-  }
-}
-
-// ================================================================================================================
 // backward: dq, dk, dv from d_o and/or the probability branches. Staged: Q, K, V, dO; outputs reuse dead tiles
 // (dV -> V, dQ -> dO, dK -> K).
 // ================================================================================================================
@@ -801,12 +692,12 @@ __global__ void __launch_bounds__(NW * 32) temporal_attn_bwd_kernel(const TAPara
 static int pad16(int row_bytes) { return row_bytes + ((16 - (row_bytes % 128)) + 128) % 128; }
 
 // ntensors: 3 (fwd: Q,K,V) or 4 (bwd: + dO). `fusable`: q, k, v are the three column blocks of one [.., 3C] buffer.
-static bool choose_geom(int D, int L, int H, int DH, int ntensors, bool need_even_p, bool fusable, TileGeom* g) {
+static bool choose_geom(int D, int L, int H, int DH, int ntensors, bool need_even_p, bool fusable, TileGeom* g,
+                        int n_batch = 0) {
   // Tile size: ~32 KB per Q/K/V set keeps 6-7 CTAs resident per SM (227 KB), which is what de-synchronises their
   // load / math / store phases (measured on B200: 61 KB tiles reach 54 % of the HBM roof at C=320, 30 KB tiles 62-75 %).
   // Tiles that would hold fewer than 4 (position, head) items get twice the budget instead of idle warps.
-  static const int env_kb = getenv("MC_TILE_KB") ? atoi(getenv("MC_TILE_KB")) : 0;  // tuning knob (KB per Q/K/V set)
-  const int base = (env_kb > 0 ? env_kb : 32) * 1024 * ntensors / 3;
+  const int base = 32 * 1024 * ntensors / 3;
   auto tbytes = [&](int P, int hg) { return (int64_t)ntensors * L * P * hg * DH * 2; };
   const int Pmin = (need_even_p && D % 2 == 0) ? 2 : 1;  // L == 8 packs two positions per item; odd D: tail pairs with itself
   const int pp = need_even_p ? 2 : 1;
@@ -819,6 +710,14 @@ static bool choose_geom(int D, int L, int H, int DH, int ntensors, bool need_eve
       while (D % (P * 2) == 0 && tbytes(P * 2, HG) <= target && P < 8) P *= 2;
     }
     if (((P + pp - 1) / pp) * HG >= 4) break;
+  }
+  // Small layers (16x16 / 8x8 latent positions at C = 1280: 10-40 MB per launch) are bound by latency, not bandwidth: a
+  // grid of less than two waves leaves SMs with one tile in flight. Halve the head group (down to 2 heads: half the
+  // warps of a CTA then idle, which costs nothing here) until the launch has at least two waves of resident CTAs.
+  if (n_batch > 0) {
+    auto ctas = [&](int hg) { return (int64_t)n_batch * (D / P) * (H / hg); };
+    auto resident = [&](int hg) { return (int64_t)148 * (227 * 1024 / (tbytes(P, hg) + 2048)); };
+    while (HG > 2 && HG % 2 == 0 && ctas(HG) < 2 * resident(HG)) HG /= 2;
   }
   g->P = P;
   g->HG = HG;
@@ -843,24 +742,6 @@ static bool is_fusable(const TAParams& prm, int C) {
 
 static bool layout_ok(const mc_temporal_layout& l) {
   return l.stride_b % 8 == 0 && l.stride_f % 8 == 0 && l.stride_p % 8 == 0;
-}
-
-template <int DH, int L, int NCW>
-static int launch_fwd_persistent(TAParams& prm, int n_tiles, cudaStream_t st) {
-  constexpr int NSTAGE = 3;
-  const int stage = (prm.g.fused ? 1 : 3) * prm.g.tensor_bytes;
-  const int smem = kHeaderBytes + NSTAGE * stage;
-  if (smem > 227 * 1024) return 1;  // caller falls back to the one-tile-per-CTA kernel
-  int per_sm = (227 * 1024) / (smem + 1024);
-  if (per_sm > 2) per_sm = 2;
-  if (per_sm < 1) per_sm = 1;
-  int grid = per_sm * 148;
-  if (grid > n_tiles) grid = n_tiles;
-  auto kern = temporal_attn_fwd_persistent_kernel<DH, L, NCW, NSTAGE>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  kern<<<grid, (NCW + 1) * 32, smem, st>>>(prm, n_tiles);
-  count_launch();
-  return check_launch("temporal_attn_fwd(persistent)");
 }
 
 // Does the runtime geometry equal the compile-time one (then the constant-address kernel can take the launch)?
@@ -895,10 +776,9 @@ static void launch_cgeom(const TAParams& prm, unsigned grid, int smem, cudaStrea
 // true if a constant-geometry instantiation took the launch (4-warp CTAs only: these tiles hold <= 8 items)
 template <int DH, int L, bool BWD>
 static bool try_launch_cgeom(const TAParams& prm, unsigned grid, int smem, int n_items, cudaStream_t st) {
-  static const int env_off = getenv("MC_NO_CGEOM") ? atoi(getenv("MC_NO_CGEOM")) : 0;  // A/B knob for profiling
   if constexpr (CGeomSet<DH, L>::enabled) {
     using S = CGeomSet<DH, L>;
-    if (env_off || n_items >= 16 || prm.H != 8) return false;
+    if (n_items >= 16 || prm.H != 8) return false;
     if (geom_matches<typename S::Fused8>(prm.g)) {
       launch_cgeom<DH, L, typename S::Fused8, BWD>(prm, grid, smem, st);
       return true;
@@ -917,22 +797,12 @@ static bool try_launch_cgeom(const TAParams& prm, unsigned grid, int smem, int n
 
 template <int DH, int L>
 static int launch_fwd(TAParams& prm, cudaStream_t st) {
-  choose_geom(prm.D, L, prm.H, DH, 3, L == 8, is_fusable(prm, prm.H * DH) && prm.o != nullptr, &prm.g);
+  choose_geom(prm.D, L, prm.H, DH, 3, L == 8, is_fusable(prm, prm.H * DH) && prm.o != nullptr, &prm.g, prm.B);
   const int smem = tile_smem(prm.g, 3);
   const int64_t grid = (int64_t)prm.B * (prm.D / prm.g.P) * (prm.H / prm.g.HG);
   const int n_items = ((prm.g.P + TACfg<DH, L>::PP - 1) / TACfg<DH, L>::PP) * prm.g.HG;
-  // The persistent / pipelined variant is kept as a measured experiment (profiles/README.md): on B200 it is not faster
-  // than 6-7 independent 30 KB CTAs per SM, because the kernel is bound by per-item instruction latency as much as by
-  // bytes in flight, and two 9-warp CTAs per SM give fewer resident warps. Opt in with MC_PERSISTENT=1.
-  static const int env_persist = getenv("MC_PERSISTENT") ? atoi(getenv("MC_PERSISTENT")) : 0;
-  if (env_persist) {
-    const int rc = (n_items >= 8) ? launch_fwd_persistent<DH, L, 8>(prm, (int)grid, st)
-                                  : launch_fwd_persistent<DH, L, 4>(prm, (int)grid, st);
-    if (rc <= 0) return rc;
-  }
-  static const int env_nw = getenv("MC_WARPS") ? atoi(getenv("MC_WARPS")) : 0;  // tuning knob
-  if (!env_nw && try_launch_cgeom<DH, L, false>(prm, (unsigned)grid, smem, n_items, st)) {
-  } else if (env_nw ? env_nw == 8 : n_items >= 16) {
+  if (try_launch_cgeom<DH, L, false>(prm, (unsigned)grid, smem, n_items, st)) {
+  } else if (n_items >= 16) {
     auto kern = temporal_attn_fwd_kernel<DH, L, 8>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     kern<<<(unsigned)grid, 8 * 32, smem, st>>>(prm);
@@ -947,7 +817,7 @@ static int launch_fwd(TAParams& prm, cudaStream_t st) {
 
 template <int DH, int L>
 static int launch_bwd(TAParams& prm, cudaStream_t st) {
-  choose_geom(prm.D, L, prm.H, DH, 4, L == 8, is_fusable(prm, prm.H * DH), &prm.g);
+  choose_geom(prm.D, L, prm.H, DH, 4, L == 8, is_fusable(prm, prm.H * DH), &prm.g, prm.B);
   const int smem = tile_smem(prm.g, 4);
   const int64_t grid = (int64_t)prm.B * (prm.D / prm.g.P) * (prm.H / prm.g.HG);
   const int n_items = ((prm.g.P + TACfg<DH, L>::PP - 1) / TACfg<DH, L>::PP) * prm.g.HG;
