@@ -7,10 +7,12 @@ __all__ = ["build_pipeline"]
 
 
 def build_pipeline(unet_config: dict, infer_config: dict, device="cuda", dtype=None, weight_seed: int = 42,
-                   state_dict=None, controlnet_kwargs=None, controlnet_state_dict=None):
+                   state_dict=None, controlnet_kwargs=None, controlnet_state_dict=None, use_cuda_graphs: bool = True):
     """UNet3D (synthetic or given weights) + DDIMScheduler + AnimationPipeline with the nine functions bound
     (what t2v_video_sample.py:36-73 does). `controlnet_kwargs` (configs/sparsectrl/*.yaml controlnet_additional_kwargs)
-    adds a SparseCtrl built with from_unet as i2v_video_sample.py:41-59 does (synthetic weights: seed + 1)."""
+    adds a SparseCtrl built with from_unet as i2v_video_sample.py:41-59 does (synthetic weights: seed + 1).
+    `use_cuda_graphs`: the no-grad UNet forwards of the sampling loop (the plain step's b=2 forward, the guided step's
+    unconditional forward) are captured once per shape and replayed (guidance._GraphedUNetForward)."""
     import torch
 
     from .guidance import bind_motionclone
@@ -37,4 +39,5 @@ def build_pipeline(unet_config: dict, infer_config: dict, device="cuda", dtype=N
         controlnet = controlnet.to(device=device, dtype=dtype).to(memory_format=torch.channels_last).eval()
     unet = unet.to(device=device, dtype=dtype).to(memory_format=torch.channels_last).eval()
     pipe = AnimationPipeline(unet=unet, scheduler=DDIMScheduler(**NOISE_SCHEDULER_KWARGS), controlnet=controlnet)
+    pipe.use_cuda_graphs = bool(use_cuda_graphs)
     return bind_motionclone(pipe, _Config(dict(infer_config)))

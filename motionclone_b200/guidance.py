@@ -252,6 +252,52 @@ def sample_video(self, eta: float = 0.0, generator=None, noisy_latents: Optional
     return self.decode_latents(noisy_latents)
 
 
+class _GraphedUNetForward:
+    """CUDA-graph replay of one no-grad `unet(sample, t, text)` shape (round-2 loop engineering): the
+    b=2 forward of a plain step is ~1 700 kernel launches whose inter-launch gaps are ~8 % of its device time; replayed
+    as ONE graph launch they disappear. Inputs live in static buffers (the timestep is a 0-dim device tensor, so the
+    sinusoidal embedding is computed inside the graph); the TMA tensor maps and kernel arguments recorded at capture keep
+    pointing at the graph's own (address-stable) pool. Weights must not be replaced after capture
+    (`pipeline.invalidate_cuda_graphs()` drops the captures)."""
+
+    def __init__(self, unet, sample, step_t, text):
+        dev = sample.device
+        self.sample = sample.clone()
+        self.step_t = step_t.detach().to(dev).clone()
+        self.text = text.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):  # warm-up on the capture stream: lazy initialisations (workspaces, caches) happen here
+                unet(self.sample, self.step_t, encoder_hidden_states=self.text)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.out = unet(self.sample, self.step_t, encoder_hidden_states=self.text).sample
+
+    def __call__(self, sample, step_t, text):
+        self.sample.copy_(sample)
+        self.step_t.copy_(step_t)
+        if text.data_ptr() != self.text.data_ptr():
+            self.text.copy_(text)
+        self.graph.replay()
+        return self.out
+
+
+def _unet_nograd(self, sample, step_t, text, step_index):
+    """No-grad UNet forward without SparseCtrl residuals: replayed from a CUDA graph when the pipeline allows it (the
+    timestep then comes from the scheduler's DEVICE copy of the schedule: no host value is baked into the graph)."""
+    if not getattr(self, "use_cuda_graphs", False) or not sample.is_cuda:
+        return self.unet(sample, step_t, encoder_hidden_states=text).sample
+    step_t = self.scheduler.timesteps[step_index]  # 0-dim int64 device tensor, no sync
+    graphs = self.__dict__.setdefault("_unet_graphs", {})
+    key = (tuple(sample.shape), sample.dtype, tuple(text.shape))
+    g = graphs.get(key)
+    if g is None:
+        g = graphs[key] = _GraphedUNetForward(self.unet, sample, step_t, text)
+    return g(sample, step_t, text)
+
+
 def single_step_video(self, noisy_latents, step_index, step_t, extra_step_kwargs):
     """:173-257."""
     cfg = self.input_config
@@ -267,9 +313,12 @@ def single_step_video(self, noisy_latents, step_index, step_t, extra_step_kwargs
         control_latents.requires_grad = True
         with torch.no_grad():
             _set_processor_mode(self, None)
-            eps_u = self.unet(noisy_latents, step_t, encoder_hidden_states=self.text_embeddings[[0]],
-                              down_block_additional_residuals=None if down is None else [r[0:1] for r in down],
-                              mid_block_additional_residual=None if mid is None else mid[0:1]).sample
+            if down is None:
+                eps_u = _unet_nograd(self, noisy_latents, step_t, self.text_embeddings[[0]], step_index)
+            else:
+                eps_u = self.unet(noisy_latents, step_t, encoder_hidden_states=self.text_embeddings[[0]],
+                                  down_block_additional_residuals=[r[0:1] for r in down],
+                                  mid_block_additional_residual=mid[0:1]).sample
         _set_processor_mode(self, "gather", {k: v[1] for k, v in rep.items()})
         eps_c = self.unet(control_latents, step_t, encoder_hidden_states=self.text_embeddings[[1]],
                           down_block_additional_residuals=None if down is None else [r[1:2] for r in down],
@@ -290,8 +339,11 @@ def single_step_video(self, noisy_latents, step_index, step_t, extra_step_kwargs
         return out.detach()
     with torch.no_grad():
         _set_processor_mode(self, None)
-        pair = self.unet(noisy_latents.expand(2, -1, -1, -1, -1), step_t, encoder_hidden_states=self.text_embeddings,
-                         down_block_additional_residuals=down, mid_block_additional_residual=mid).sample
+        if down is None:
+            pair = _unet_nograd(self, noisy_latents.expand(2, -1, -1, -1, -1), step_t, self.text_embeddings, step_index)
+        else:
+            pair = self.unet(noisy_latents.expand(2, -1, -1, -1, -1), step_t, encoder_hidden_states=self.text_embeddings,
+                             down_block_additional_residuals=down, mid_block_additional_residual=mid).sample
         out = self.scheduler.customized_step_fused(pair[[1]], pair[[0]], cfg_scale, step_index, noisy_latents,
                                                    score=None, **extra_step_kwargs)
     return out.detach()

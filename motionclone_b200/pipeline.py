@@ -90,6 +90,10 @@ class AnimationPipeline:
     def progress_bar(self, total=None):
         yield _Bar()
 
+    def invalidate_cuda_graphs(self):
+        """Drop the captured UNet forwards (call after replacing or editing weights; see guidance._GraphedUNetForward)."""
+        self.__dict__.pop("_unet_graphs", None)
+
     def set_prompt_embeds(self, embeds: torch.Tensor):
         """[2, 77, cross_attention_dim] = [uncond, cond] (the order _encode_prompt returns, :139 of the functions file)."""
         self.prompt_embeds = embeds

@@ -193,3 +193,27 @@ def test_latents_vs_same_device_oracle(run):
     print(run["case"], f"vs fp16 oracle on device: index mismatches {mism}/{tot}; per-step latent rel err {rels}")
     assert mism / tot < 0.02
     assert rels[-1] < 5e-2
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    """The captured no-grad UNet forwards (plain step, unconditional forward of guided steps) replay the same kernels on
+    the same data: the sampled latents must equal the eager launches bit for bit."""
+    import motionclone_b200 as mc
+    dev = torch.device("cuda:0")
+    g, meta = _load("tiny16")
+    icfg = dict(meta["infer"])
+    inp = synthetic_inputs(icfg["video_length"], icfg["height"], icfg["width"], UNET_TINY_CONFIG["cross_attention_dim"],
+                           meta["input_seed"])
+    icfg.update(video_latents=inp["clip_latents"].half(), video_noise=inp["clip_noise"].half(), new_prompt="synthetic")
+    outs = []
+    for graphs in (False, True):
+        pipe = mc.build_pipeline(UNET_TINY_CONFIG, icfg, device=dev, weight_seed=meta["weight_seed"], use_cuda_graphs=graphs)
+        pipe.set_prompt_embeds(inp["text_embeddings"].to(dev, torch.float16))
+        pipe.obtain_motion_representation(motion_representation_path=None)
+        finals = [pipe.sample_video(noisy_latents=inp["noisy_latents"].to(dev, torch.float16), return_latents=True).clone()
+                  for _ in range(2)]  # second sample replays the graphs captured by the first
+        assert torch.equal(finals[0], finals[1])
+        outs.append(finals[1])
+        assert ("_unet_graphs" in pipe.__dict__) == graphs
+    assert torch.equal(outs[0], outs[1])
+
