@@ -409,7 +409,9 @@ def run_own_arm(args):
     # roofline leg: ONE more sample with a CUDA-event pair around every launch of this package's attention kernels (on the
     # launching stream). Kept out of the timed regions above: ~8 000 event records per sample cost ~3 % of the step.
     ops.TIMER = ops.KernelTimer()
+    graphs_on, pipe.use_cuda_graphs = pipe.use_cuda_graphs, False  # every launch through Python, so every one gets its events
     step_resident(args.warmup)
+    pipe.use_cuda_graphs = graphs_on
     ksum = ops.TIMER.summary()
     ops.TIMER = None
 

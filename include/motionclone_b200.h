@@ -44,6 +44,9 @@ const char* mc_last_error(void);
 /* number of kernels this library has enqueued since load / since the last reset (bench.py "gpu_launches") */
 uint64_t mc_launch_count(void);
 void mc_reset_launch_count(void);
+/* a CUDA-graph replay re-executes kernels this library enqueued during capture without passing through its entry points:
+ * the host adds their number (the counter's delta over the capture) per replay */
+void mc_add_launch_count(uint64_t n);
 
 /*
  * Fused temporal self-attention forward: O = softmax(scale * Q K^T) V over the frame axis for every

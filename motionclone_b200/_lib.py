@@ -22,7 +22,7 @@ class MotionCloneKernelError(RuntimeError):
 
 _lib = None
 
-EXPORTS = ("mc_abi_version", "mc_last_error", "mc_launch_count", "mc_reset_launch_count", "mc_temporal_attn_fwd",
+EXPORTS = ("mc_abi_version", "mc_last_error", "mc_launch_count", "mc_reset_launch_count", "mc_add_launch_count", "mc_temporal_attn_fwd",
            "mc_temporal_attn_bwd", "mc_top1_rows", "mc_motion_loss_fwd", "mc_motion_loss_bwd", "mc_cfg_ddim_step",
            "mc_add_noise", "mc_groupnorm_workspace_bytes", "mc_groupnorm_nhwc", "mc_layernorm", "mc_geglu", "mc_groupnorm_nhwc_stats", "mc_groupnorm_nhwc_bwd", "mc_layernorm_bwd",
            "mc_geglu_bwd", "mc_bias_residual_add", "mc_cross_attn_fwd", "mc_cross_attn_bwd_dq",
@@ -43,6 +43,8 @@ def lib() -> ctypes.CDLL:
     L.mc_last_error.restype = c_char_p
     L.mc_launch_count.restype = c_uint64
     L.mc_reset_launch_count.restype = None
+    L.mc_add_launch_count.restype = None
+    L.mc_add_launch_count.argtypes = [c_uint64]
     L.mc_temporal_attn_fwd.restype = c_int
     L.mc_temporal_attn_fwd.argtypes = [P, P, P, TemporalLayout, P, TemporalLayout, P, P, P, P, P,
                                        c_int, c_int, c_int, c_int, c_int, c_float, P]
@@ -107,3 +109,7 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     lib().mc_reset_launch_count()
+
+
+def add_launch_count(n: int) -> None:
+    lib().mc_add_launch_count(int(n))

@@ -35,3 +35,4 @@ extern "C" int mc_abi_version(void) { return MC_ABI_VERSION; }
 extern "C" const char* mc_last_error(void) { return mc::g_err; }
 extern "C" uint64_t mc_launch_count(void) { return mc::g_launches.load(std::memory_order_relaxed); }
 extern "C" void mc_reset_launch_count(void) { mc::g_launches.store(0, std::memory_order_relaxed); }
+extern "C" void mc_add_launch_count(uint64_t n) { mc::g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Sequence, Union
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .temporal import MotionRecordProcessor, VersatileAttention
 from .unet3d import UNet3DConditionModel, UNet3DConditionOutput  # noqa: F401  (re-export, as the reference does)
 
@@ -272,8 +272,10 @@ class _GraphedUNetForward:
                 unet(self.sample, self.step_t, encoder_hidden_states=self.text)
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.out = unet(self.sample, self.step_t, encoder_hidden_states=self.text).sample
+        self.n_kernels = _lib.launch_count() - n0  # this library's kernels inside the graph (counted again per replay)
 
     def __call__(self, sample, step_t, text):
         self.sample.copy_(sample)
@@ -281,6 +283,7 @@ class _GraphedUNetForward:
         if text.data_ptr() != self.text.data_ptr():
             self.text.copy_(text)
         self.graph.replay()
+        _lib.add_launch_count(self.n_kernels)
         return self.out
 
 
