@@ -133,17 +133,21 @@ struct FABwdCfg {
   static constexpr int DHP = TA::DHP;
   static constexpr bool AT = DHP <= 48;   // resident operand tiles live in tensor memory as A operands
   static constexpr int KP = DHP / 2;      // packed columns of a resident [128][DHP] fp16 tile
-  // dQ kernel. shared memory: Q, dO (only staging when AT); K, V double-buffered.
-  static constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TA::BYTES, DQ_OFF_K = 2 * TA::BYTES, DQ_OFF_V = DQ_OFF_K + 2 * TB::BYTES;
-  static constexpr int DQ_OFF_BAR = DQ_OFF_V + 2 * TB::BYTES, DQ_SMEM = DQ_OFF_BAR + 128 + 1024;
+  // Streamed-tile ring depth. A stage is refilled when the MMAs that read it have completed, i.e. NS - 1 tiles before it is
+  // needed again: with 2 stages the TMA round trip (~1 us) sat on the critical path of every tile (round-2 ncu: 58 % of
+  // stall samples were warps parked on mbarriers with the tensor pipe half idle).
+  static constexpr int NS = DHP <= 48 ? 4 : (DHP <= 80 ? 3 : 2);
+  // dQ kernel. shared memory: Q, dO (only staging when AT); K, V ring.
+  static constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TA::BYTES, DQ_OFF_K = 2 * TA::BYTES, DQ_OFF_V = DQ_OFF_K + NS * TB::BYTES;
+  static constexpr int DQ_OFF_BAR = DQ_OFF_V + NS * TB::BYTES, DQ_SMEM = DQ_OFF_BAR + 256 + 1024;
   // tensor memory: S [0,64) dP [64,128) dS(fp16 pairs) [128,160) dQ [160,160+DHP) [Q, dO packed when AT]
   static constexpr int DQ_DS = 128, DQ_ACC = 160, DQ_QT = 160 + DHP, DQ_DOT = DQ_QT + KP;
   static constexpr int DQ_NEED = AT ? DQ_DOT + KP : DQ_ACC + DHP;
   static constexpr int DQ_TCOLS = DQ_NEED <= 256 ? 256 : 512;
   static constexpr int DQ_CTAS = (DQ_TCOLS == 256 && 2 * DQ_SMEM <= 227 * 1024) ? 2 : 1;
   // dKV kernel. shared memory: K, V resident; Q, dO double-buffered.
-  static constexpr int KV_OFF_K = 0, KV_OFF_V = TA::BYTES, KV_OFF_Q = 2 * TA::BYTES, KV_OFF_DO = KV_OFF_Q + 2 * TB::BYTES;
-  static constexpr int KV_OFF_BAR = KV_OFF_DO + 2 * TB::BYTES, KV_SMEM = KV_OFF_BAR + 128 + 1024;
+  static constexpr int KV_OFF_K = 0, KV_OFF_V = TA::BYTES, KV_OFF_Q = 2 * TA::BYTES, KV_OFF_DO = KV_OFF_Q + NS * TB::BYTES;
+  static constexpr int KV_OFF_BAR = KV_OFF_DO + NS * TB::BYTES, KV_SMEM = KV_OFF_BAR + 256 + 1024;
   // tensor memory: S^T [0,64) dP^T [64,128) (P^T / dS^T are written back over them as fp16 pairs) dV, dK [V packed when AT]
   static constexpr int DV_COL = 128, DK_COL = 128 + DHP, KV_VT = 128 + 2 * DHP;
   static constexpr int KV_NEED = AT ? KV_VT + KP : KV_VT;
@@ -197,17 +201,18 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem + X::DQ_OFF_Q;
   uint8_t* sDO = smem + X::DQ_OFF_DO;
-  uint8_t* sK = smem + X::DQ_OFF_K;   // 2 stages
-  uint8_t* sV = smem + X::DQ_OFF_V;   // 2 stages
+  uint8_t* sK = smem + X::DQ_OFF_K;   // NS stages
+  uint8_t* sV = smem + X::DQ_OFF_V;   // NS stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X::DQ_OFF_BAR);
   uint64_t* bar_q = bars + 0;        // Q and dO landed
-  uint64_t* bar_kv = bars + 1;       // [2] K_j, V_j landed in stage j & 1
-  uint64_t* sdp_full = bars + 3;     // S_j, dP_j in TMEM
-  uint64_t* sdp_free = bars + 4;     // copied to registers (8 warp arrivals)
-  uint64_t* ds_full = bars + 5;      // dS_j in TMEM (8 warp arrivals)
-  uint64_t* dq_done = bars + 6;      // dQ += dS_j K_j completed
-  uint64_t* a_ready = bars + 7;      // Q, dO copied into tensor memory (8 warp arrivals; AT only)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* sdp_full = bars + 1;     // S_j, dP_j in TMEM
+  uint64_t* sdp_free = bars + 2;     // copied to registers (8 warp arrivals)
+  uint64_t* ds_full = bars + 3;      // dS_j in TMEM (8 warp arrivals)
+  uint64_t* dq_done = bars + 4;      // dQ += dS_j K_j completed
+  uint64_t* a_ready = bars + 5;      // Q, dO copied into tensor memory (8 warp arrivals; AT only)
+  uint64_t* bar_kv = bars + 8;       // [NS] K_j, V_j landed in stage j % NS
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + X::NS);
+  constexpr int NS = X::NS;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -217,9 +222,10 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
   if (warp == kBComputeWarps) {
     tmem_alloc<X::DQ_TCOLS>(tmem_slot);
     if (lane == 0) {
-      mbar_init(bar_q, 1), mbar_init(bar_kv, 1), mbar_init(bar_kv + 1, 1), mbar_init(sdp_full, 1);
+      mbar_init(bar_q, 1), mbar_init(sdp_full, 1);
       mbar_init(sdp_free, kBComputeWarps), mbar_init(ds_full, kBComputeWarps), mbar_init(dq_done, 1);
       mbar_init(a_ready, kBComputeWarps);
+      for (int i = 0; i < NS; ++i) mbar_init(bar_kv + i, 1);
       fence_mbar_init();
     }
   }
@@ -242,7 +248,7 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
       mbar_arrive_expect_tx(bar_q, 2 * TA::BYTES);
       tma_load_tile<DH, 128>(sQ, &mq128, &mq32, bar_q, q0, h, b);
       tma_load_tile<DH, 128>(sDO, &mdo128, &mdo32, bar_q, q0, h, b);
-      for (int j = 0; j < 2 && j < T_tiles; ++j) {
+      for (int j = 0; j < NS && j < T_tiles; ++j) {
         mbar_arrive_expect_tx(bar_kv + j, 2 * TB::BYTES);
         tma_load_tile<DH, kBT>(sK + j * TB::BYTES, &mk128, &mk32, bar_kv + j, j * kBT, h, b);
         tma_load_tile<DH, kBT>(sV + j * TB::BYTES, &mv128, &mv32, bar_kv + j, j * kBT, h, b);
@@ -254,10 +260,11 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
       issue_sdp(0);
       umma_commit(sdp_full);
       for (int j = 0; j < T_tiles; ++j) {
-        const uint32_t ph = j & 1, st = j & 1;
+        const uint32_t ph = j & 1;
+        const int st = j % NS;
         if (j + 1 < T_tiles) {
-          const int sn = (j + 1) & 1;
-          mbar_wait(bar_kv + sn, ((j + 1) >> 1) & 1);
+          const int sn = (j + 1) % NS;
+          mbar_wait(bar_kv + sn, ((j + 1) / NS) & 1);
           mbar_wait(sdp_free, ph);
           tc_fence_after();
           issue_sdp(sn);
@@ -268,11 +275,11 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
         issue_ab64_ts<DH>(tmem_base + X::DQ_ACC, [&](int ks) { return tmem_base + X::DQ_DS + ks * 8; },
                           smem_u32(sK + st * TB::BYTES), j > 0);
         umma_commit(dq_done);
-        if (j + 2 < T_tiles) {
-          mbar_wait(dq_done, ph);  // K_j / V_j consumed: refill the stage with tile j + 2
+        if (j + NS < T_tiles) {
+          mbar_wait(dq_done, ph);  // K_j / V_j consumed: refill the stage with tile j + NS
           mbar_arrive_expect_tx(bar_kv + st, 2 * TB::BYTES);
-          tma_load_tile<DH, kBT>(sK + st * TB::BYTES, &mk128, &mk32, bar_kv + st, (j + 2) * kBT, h, b);
-          tma_load_tile<DH, kBT>(sV + st * TB::BYTES, &mv128, &mv32, bar_kv + st, (j + 2) * kBT, h, b);
+          tma_load_tile<DH, kBT>(sK + st * TB::BYTES, &mk128, &mk32, bar_kv + st, (j + NS) * kBT, h, b);
+          tma_load_tile<DH, kBT>(sV + st * TB::BYTES, &mv128, &mv32, bar_kv + st, (j + NS) * kBT, h, b);
         }
       }
     }
@@ -351,16 +358,17 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem + X::KV_OFF_K;
   uint8_t* sV = smem + X::KV_OFF_V;
-  uint8_t* sQ = smem + X::KV_OFF_Q;    // 2 stages
-  uint8_t* sDO = smem + X::KV_OFF_DO;  // 2 stages
+  uint8_t* sQ = smem + X::KV_OFF_Q;    // NS stages
+  uint8_t* sDO = smem + X::KV_OFF_DO;  // NS stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X::KV_OFF_BAR);
   uint64_t* bar_kv = bars + 0;      // K, V landed
-  uint64_t* bar_q = bars + 1;       // [2] Q_i, dO_i landed in stage i & 1
-  uint64_t* st_full = bars + 3;     // S^T_i, dP^T_i in TMEM
-  uint64_t* pt_full = bars + 4;     // P^T_i, dS^T_i written back to TMEM, S^T_i / dP^T_i consumed (8 warp arrivals)
-  uint64_t* dkv_done = bars + 5;    // dV, dK updates of tile i completed
-  uint64_t* a_ready = bars + 6;     // V copied into tensor memory (4 warp arrivals; AT only)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* st_full = bars + 1;     // S^T_i, dP^T_i in TMEM
+  uint64_t* pt_full = bars + 2;     // P^T_i, dS^T_i written back to TMEM, S^T_i / dP^T_i consumed (8 warp arrivals)
+  uint64_t* dkv_done = bars + 3;    // dV, dK updates of tile i completed
+  uint64_t* a_ready = bars + 4;     // V copied into tensor memory (4 warp arrivals; AT only)
+  uint64_t* bar_q = bars + 8;       // [NS] Q_i, dO_i landed in stage i % NS
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + X::NS);
+  constexpr int NS = X::NS;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -370,8 +378,9 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
   if (warp == kBComputeWarps) {
     tmem_alloc<X::KV_TCOLS>(tmem_slot);
     if (lane == 0) {
-      mbar_init(bar_kv, 1), mbar_init(bar_q, 1), mbar_init(bar_q + 1, 1), mbar_init(st_full, 1);
+      mbar_init(bar_kv, 1), mbar_init(st_full, 1);
       mbar_init(pt_full, kBComputeWarps), mbar_init(dkv_done, 1), mbar_init(a_ready, 4);
+      for (int i = 0; i < NS; ++i) mbar_init(bar_q + i, 1);
       fence_mbar_init();
     }
   }
@@ -393,7 +402,7 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
       mbar_arrive_expect_tx(bar_kv, 2 * TA::BYTES);
       tma_load_tile<DH, 128>(sK, &mk128, &mk32, bar_kv, k0, h, b);
       tma_load_tile<DH, 128>(sV, &mv128, &mv32, bar_kv, k0, h, b);
-      for (int i = 0; i < 2 && i < T_tiles; ++i) {
+      for (int i = 0; i < NS && i < T_tiles; ++i) {
         mbar_arrive_expect_tx(bar_q + i, 2 * TB::BYTES);
         tma_load_tile<DH, kBT>(sQ + i * TB::BYTES, &mq128, &mq32, bar_q + i, i * kBT, h, b);
         tma_load_tile<DH, kBT>(sDO + i * TB::BYTES, &mdo128, &mdo32, bar_q + i, i * kBT, h, b);
@@ -405,7 +414,8 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
       issue_st(0);
       umma_commit(st_full);
       for (int i = 0; i < T_tiles; ++i) {
-        const uint32_t ph = i & 1, st = i & 1;
+        const uint32_t ph = i & 1;
+        const int st = i % NS;
         mbar_wait(pt_full, ph);  // P^T_i, dS^T_i in tensor memory (every thread has consumed S^T_i, dP^T_i)
         tc_fence_after();
         issue_ab64_ts<DH>(tmem_base + X::DV_COL, [&](int ks) { return tmem_base + a_cols(ks); },
@@ -414,17 +424,17 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
                           smem_u32(sQ + st * TB::BYTES), i > 0);
         umma_commit(dkv_done);
         if (i + 1 < T_tiles) {  // next S^T, dP^T right behind (in-order pipe: P^T_i / dS^T_i are read before the overwrite)
-          const int sn = (i + 1) & 1;
-          mbar_wait(bar_q + sn, ((i + 1) >> 1) & 1);
+          const int sn = (i + 1) % NS;
+          mbar_wait(bar_q + sn, ((i + 1) / NS) & 1);
           tc_fence_after();
           issue_st(sn);
           umma_commit(st_full);
         }
-        if (i + 2 < T_tiles) {
+        if (i + NS < T_tiles) {
           mbar_wait(dkv_done, ph);
           mbar_arrive_expect_tx(bar_q + st, 2 * TB::BYTES);
-          tma_load_tile<DH, kBT>(sQ + st * TB::BYTES, &mq128, &mq32, bar_q + st, (i + 2) * kBT, h, b);
-          tma_load_tile<DH, kBT>(sDO + st * TB::BYTES, &mdo128, &mdo32, bar_q + st, (i + 2) * kBT, h, b);
+          tma_load_tile<DH, kBT>(sQ + st * TB::BYTES, &mq128, &mq32, bar_q + st, (i + NS) * kBT, h, b);
+          tma_load_tile<DH, kBT>(sDO + st * TB::BYTES, &mdo128, &mdo32, bar_q + st, (i + NS) * kBT, h, b);
         }
       }
     }
