@@ -330,7 +330,8 @@ def run_own_arm(args):
         if kind == "image":
             infer["video_pixels"] = cond["clip_pixels"]
     t0 = time.time()
-    pipe = mc.build_pipeline(UNET_SD15_CONFIG, infer, device=dev, weight_seed=42, controlnet_kwargs=cn_kwargs)
+    pipe = mc.build_pipeline(UNET_SD15_CONFIG, infer, device=dev, weight_seed=42, controlnet_kwargs=cn_kwargs,
+                             use_cuda_graphs=not args.no_cuda_graphs)
     log(f"[rank {rank}] model built in {time.time() - t0:.0f}s")
     # weak scaling: every rank denoises its own samples (seed 1000 + global sample index) of ONE shared reference clip
     pipe.set_prompt_embeds(h(inp["text_embeddings"]))
@@ -477,7 +478,8 @@ def run_own_arm(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic",
             "config": config_block(infer, workload, world),
-            "arm": f"replica x{world} (independent samples), one NCCL broadcast of the motion representation",
+            "arm": f"replica x{world} (independent samples), one NCCL broadcast of the motion representation; "
+                   f"cuda graphs {'on' if pipe.use_cuda_graphs else 'off'}",
             "init": {"nccl_init_ms": nccl_init_ms, "broadcast_ms": bcast_ms, "broadcast_bytes": int(rep_host.numel())},
             "e2e": {"value": e2e, "unit": UNIT,
                     "h2d_bytes_per_step": lat_bytes + text_host[0].numel() * 2 + rep_host.numel(),
@@ -497,6 +499,7 @@ def main():
     ap.add_argument("--ddim-steps", type=int, default=50, help="profiling only: anything but 50 is not a bench value")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-cuda-graphs", action="store_true", help="A/B: launch the no-grad UNet forwards eagerly")
     ap.add_argument("--ref-budget", type=float, default=240.0, help="seconds of CPU work for --impl reference")
     ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work for the cpu_baseline leg")
     args = ap.parse_args()
