@@ -10,7 +10,7 @@
 //   dKV kernel : CTA = 128 keys,   streams 64-query tiles:  S^T = K Q^T, dP^T = V dO^T (M=128 keys, N=64 q)
 //                -> P^T, dS^T -> smem -> dV += P^T dO, dK += dS^T Q
 // Both kernels: 8 compute warps (thread = TMEM lane = tile row, the two warps that share a lane quarter split the 64
-// columns) + 1 producer warp whose lane 0 issues every TMA load and MMA; accumulators in TMEM; 2 CTAs per SM where the
+// columns) + an MMA warp and a TMA warp (one thread each: MMA issue never waits behind a ring refill); accumulators in TMEM; 2 CTAs per SM where the
 // TMEM budget allows. Every streamed [rows][DH] tile serves two GEMMs through two descriptors - K-major where DH is
 // contracted (S, dP), MN-major where the rows are (dS K, P^T dO, dS^T Q) - so nothing is transposed or copied twice.
 // The tiles the threads produce (dS, P^T, dS^T) never touch shared memory: they go back into tensor memory as fp16 pairs
@@ -30,7 +30,8 @@ namespace mc {
 constexpr int kBM = 128;         // resident rows per CTA (UMMA M)
 constexpr int kBT = 64;          // streamed tile height (keys in the dQ kernel, queries in the dKV kernel)
 constexpr int kBComputeWarps = 8;
-constexpr int kBThreads = (kBComputeWarps + 1) * 32;
+constexpr int kBMmaWarp = kBComputeWarps, kBTmaWarp = kBComputeWarps + 1;  // lane 0 of each: MMA issue / TMA loads
+constexpr int kBThreads = (kBComputeWarps + 2) * 32;
 
 struct FABwdParams {
   const float* lse2;   // [B][H][Npad]  lse * log2(e)      (padding: 0)
@@ -219,7 +220,7 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
   const int q0 = qt * kBM, N = prm.N;
   const int T_tiles = (N + kBT - 1) / kBT;
 
-  if (warp == kBComputeWarps) {
+  if (warp == kBMmaWarp) {
     tmem_alloc<X::DQ_TCOLS>(tmem_slot);
     if (lane == 0) {
       mbar_init(bar_q, 1), mbar_init(sdp_full, 1);
@@ -234,7 +235,27 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == kBComputeWarps) {
+  if (warp == kBTmaWarp) {
+    // ---- TMA warp: resident tiles, then the K / V ring (a stage is refilled as soon as the MMAs that read it are done) ----
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q, 2 * TA::BYTES);
+      tma_load_tile<DH, 128>(sQ, &mq128, &mq32, bar_q, q0, h, b);
+      tma_load_tile<DH, 128>(sDO, &mdo128, &mdo32, bar_q, q0, h, b);
+      for (int j = 0; j < NS && j < T_tiles; ++j) {
+        mbar_arrive_expect_tx(bar_kv + j, 2 * TB::BYTES);
+        tma_load_tile<DH, kBT>(sK + j * TB::BYTES, &mk128, &mk32, bar_kv + j, j * kBT, h, b);
+        tma_load_tile<DH, kBT>(sV + j * TB::BYTES, &mv128, &mv32, bar_kv + j, j * kBT, h, b);
+      }
+      for (int j = 0; j + NS < T_tiles; ++j) {
+        const int st = j % NS;
+        mbar_wait(dq_done, j & 1);  // K_j / V_j consumed
+        mbar_arrive_expect_tx(bar_kv + st, 2 * TB::BYTES);
+        tma_load_tile<DH, kBT>(sK + st * TB::BYTES, &mk128, &mk32, bar_kv + st, (j + NS) * kBT, h, b);
+        tma_load_tile<DH, kBT>(sV + st * TB::BYTES, &mv128, &mv32, bar_kv + st, (j + NS) * kBT, h, b);
+      }
+    }
+  } else if (warp == kBMmaWarp) {
+    // ---- MMA warp: one thread issues every tcgen05.mma ----
     if (lane == 0) {
       auto issue_sdp = [&](int stage) {
         if constexpr (X::AT) {
@@ -245,14 +266,6 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
           issue_qk64<DH>(tmem_base + 64, smem_u32(sDO), smem_u32(sV + stage * TB::BYTES));
         }
       };
-      mbar_arrive_expect_tx(bar_q, 2 * TA::BYTES);
-      tma_load_tile<DH, 128>(sQ, &mq128, &mq32, bar_q, q0, h, b);
-      tma_load_tile<DH, 128>(sDO, &mdo128, &mdo32, bar_q, q0, h, b);
-      for (int j = 0; j < NS && j < T_tiles; ++j) {
-        mbar_arrive_expect_tx(bar_kv + j, 2 * TB::BYTES);
-        tma_load_tile<DH, kBT>(sK + j * TB::BYTES, &mk128, &mk32, bar_kv + j, j * kBT, h, b);
-        tma_load_tile<DH, kBT>(sV + j * TB::BYTES, &mv128, &mv32, bar_kv + j, j * kBT, h, b);
-      }
       if constexpr (X::AT) mbar_wait(a_ready, 0);
       else mbar_wait(bar_q, 0);
       mbar_wait(bar_kv, 0);
@@ -275,12 +288,6 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
         issue_ab64_ts<DH>(tmem_base + X::DQ_ACC, [&](int ks) { return tmem_base + X::DQ_DS + ks * 8; },
                           smem_u32(sK + st * TB::BYTES), j > 0);
         umma_commit(dq_done);
-        if (j + NS < T_tiles) {
-          mbar_wait(dq_done, ph);  // K_j / V_j consumed: refill the stage with tile j + NS
-          mbar_arrive_expect_tx(bar_kv + st, 2 * TB::BYTES);
-          tma_load_tile<DH, kBT>(sK + st * TB::BYTES, &mk128, &mk32, bar_kv + st, (j + NS) * kBT, h, b);
-          tma_load_tile<DH, kBT>(sV + st * TB::BYTES, &mv128, &mv32, bar_kv + st, (j + NS) * kBT, h, b);
-        }
       }
     }
   } else {
@@ -337,7 +344,7 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kBComputeWarps) {
+  if (warp == kBMmaWarp) {
     __syncwarp();
     tmem_dealloc<X::DQ_TCOLS>(tmem_base);
   }
@@ -375,7 +382,7 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
   const int k0 = kt * kBM, N = prm.N;
   const int T_tiles = (N + kBT - 1) / kBT;
 
-  if (warp == kBComputeWarps) {
+  if (warp == kBMmaWarp) {
     tmem_alloc<X::KV_TCOLS>(tmem_slot);
     if (lane == 0) {
       mbar_init(bar_kv, 1), mbar_init(st_full, 1);
@@ -392,13 +399,8 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
   // packed columns [32 hh, 32 hh + 16) of the region their S^T / dP^T values came from
   auto a_cols = [](int ks) { return (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8); };
 
-  if (warp == kBComputeWarps) {
+  if (warp == kBTmaWarp) {
     if (lane == 0) {
-      auto issue_st = [&](int stage) {
-        issue_qk64<DH>(tmem_base, smem_u32(sK), smem_u32(sQ + stage * TB::BYTES));
-        if constexpr (X::AT) issue_qk64_ts<DH>(tmem_base + 64, tmem_base + X::KV_VT, smem_u32(sDO + stage * TB::BYTES));
-        else issue_qk64<DH>(tmem_base + 64, smem_u32(sV), smem_u32(sDO + stage * TB::BYTES));
-      };
       mbar_arrive_expect_tx(bar_kv, 2 * TA::BYTES);
       tma_load_tile<DH, 128>(sK, &mk128, &mk32, bar_kv, k0, h, b);
       tma_load_tile<DH, 128>(sV, &mv128, &mv32, bar_kv, k0, h, b);
@@ -407,6 +409,21 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
         tma_load_tile<DH, kBT>(sQ + i * TB::BYTES, &mq128, &mq32, bar_q + i, i * kBT, h, b);
         tma_load_tile<DH, kBT>(sDO + i * TB::BYTES, &mdo128, &mdo32, bar_q + i, i * kBT, h, b);
       }
+      for (int i = 0; i + NS < T_tiles; ++i) {
+        const int st = i % NS;
+        mbar_wait(dkv_done, i & 1);  // Q_i / dO_i consumed
+        mbar_arrive_expect_tx(bar_q + st, 2 * TB::BYTES);
+        tma_load_tile<DH, kBT>(sQ + st * TB::BYTES, &mq128, &mq32, bar_q + st, (i + NS) * kBT, h, b);
+        tma_load_tile<DH, kBT>(sDO + st * TB::BYTES, &mdo128, &mdo32, bar_q + st, (i + NS) * kBT, h, b);
+      }
+    }
+  } else if (warp == kBMmaWarp) {
+    if (lane == 0) {
+      auto issue_st = [&](int stage) {
+        issue_qk64<DH>(tmem_base, smem_u32(sK), smem_u32(sQ + stage * TB::BYTES));
+        if constexpr (X::AT) issue_qk64_ts<DH>(tmem_base + 64, tmem_base + X::KV_VT, smem_u32(sDO + stage * TB::BYTES));
+        else issue_qk64<DH>(tmem_base + 64, smem_u32(sV), smem_u32(sDO + stage * TB::BYTES));
+      };
       mbar_wait(bar_kv, 0);
       if constexpr (X::AT) mbar_wait(a_ready, 0);
       mbar_wait(bar_q, 0);
@@ -429,12 +446,6 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
           tc_fence_after();
           issue_st(sn);
           umma_commit(st_full);
-        }
-        if (i + NS < T_tiles) {
-          mbar_wait(dkv_done, ph);
-          mbar_arrive_expect_tx(bar_q + st, 2 * TB::BYTES);
-          tma_load_tile<DH, kBT>(sQ + st * TB::BYTES, &mq128, &mq32, bar_q + st, (i + NS) * kBT, h, b);
-          tma_load_tile<DH, kBT>(sDO + st * TB::BYTES, &mdo128, &mdo32, bar_q + st, (i + NS) * kBT, h, b);
         }
       }
     }
@@ -499,7 +510,7 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kBComputeWarps) {
+  if (warp == kBMmaWarp) {
     __syncwarp();
     tmem_dealloc<X::KV_TCOLS>(tmem_base);
   }
