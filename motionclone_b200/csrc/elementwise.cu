@@ -1,6 +1,8 @@
 // Fused elementwise / reduction kernels of the guided step (sm_100a): CFG combine + score-guided DDIM update,
 // add_noise, stand-alone top-1, and the motion-guidance loss with its closed-form gradient.
 // All are HBM / launch-latency bound: 128-bit coalesced accesses, grid sized in multiples of the SM count.
+#include <mutex>
+
 #include "mc_common.cuh"
 
 namespace mc {
@@ -210,13 +212,19 @@ __global__ void __launch_bounds__(256) motion_loss_bwd_kernel(LossArgs a, const 
     dc[i] = __float2half_rn(g * (__half2float(cur[i]) - __half2float(ref[i])));
 }
 
+// Ticket word of the last-CTA reduction, ONE PER DEVICE (zero-initialised once, re-zeroed by the kernel). The loss kernels
+// of one device must not run concurrently on two streams (the guided step issues them on one stream).
 static unsigned int* loss_counter() {
-  static unsigned int* ptr = nullptr;  // per-process scratch word, zero-initialised once, re-zeroed by the kernel
-  if (ptr == nullptr) {
-    if (cudaMalloc(&ptr, sizeof(unsigned int)) != cudaSuccess) return nullptr;
-    cudaMemset(ptr, 0, sizeof(unsigned int));
+  static unsigned int* ptrs[64] = {};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (ptrs[dev] == nullptr) {
+    if (cudaMalloc(&ptrs[dev], sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    cudaMemset(ptrs[dev], 0, sizeof(unsigned int));
   }
-  return ptr;
+  return ptrs[dev];
 }
 
 static unsigned grid_for(int64_t nvec, int threads) {
