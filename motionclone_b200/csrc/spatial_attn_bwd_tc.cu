@@ -321,8 +321,8 @@ spatial_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq128, const __gr
       if (lane == 0) mbar_arrive(sdp_free);
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {  // dS = P o (scale dP - scale D)
-        const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), c, nl2));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), c, nl2));
+        float p0, p1;
+        ex2_pair(i >> 1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), c, nl2, p0, p1);
         s[i >> 1] = pack_half2(p0 * fmaf(__uint_as_float(dp[i]), sc, nD), p1 * fmaf(__uint_as_float(dp[i + 1]), sc, nD));
       }
       if (j > 0) {

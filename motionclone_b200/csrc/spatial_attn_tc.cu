@@ -258,8 +258,8 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int i = 0; i < BN; i += 2) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), c, negm));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), c, negm));
+        float p0, p1;
+        ex2_pair(i >> 1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), c, negm, p0, p1);
         if constexpr (!X::PAD_SUM) l0 += p0, l1 += p1;
         s[i >> 1] = pack_half2(p0, p1);
       }
