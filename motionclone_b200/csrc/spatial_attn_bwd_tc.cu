@@ -148,7 +148,9 @@ struct FABwdCfg {
   static constexpr int DQ_CTAS = (DQ_TCOLS == 256 && 2 * DQ_SMEM <= 227 * 1024) ? 2 : 1;
   // dKV kernel. shared memory: K, V resident; Q, dO double-buffered.
   static constexpr int KV_OFF_K = 0, KV_OFF_V = TA::BYTES, KV_OFF_Q = 2 * TA::BYTES, KV_OFF_DO = KV_OFF_Q + NS * TB::BYTES;
-  static constexpr int KV_OFF_BAR = KV_OFF_DO + NS * TB::BYTES, KV_SMEM = KV_OFF_BAR + 256 + 1024;
+  // per-query statistics of the streamed tile ride the same ring: 64 x (lse2, scale D) fp32 = 512 B per stage
+  static constexpr int KV_OFF_BAR = KV_OFF_DO + NS * TB::BYTES, KV_OFF_ST = KV_OFF_BAR + 256;
+  static constexpr int KV_SMEM = KV_OFF_ST + NS * 512 + 1024;
   // tensor memory: S^T [0,64) dP^T [64,128) (P^T / dS^T are written back over them as fp16 pairs) dV, dK [V packed when AT]
   static constexpr int DV_COL = 128, DK_COL = 128 + DHP, KV_VT = 128 + 2 * DHP;
   static constexpr int KV_NEED = AT ? KV_VT + KP : KV_VT;
@@ -367,6 +369,7 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
   uint8_t* sV = smem + X::KV_OFF_V;
   uint8_t* sQ = smem + X::KV_OFF_Q;    // NS stages
   uint8_t* sDO = smem + X::KV_OFF_DO;  // NS stages
+  uint8_t* sST = smem + X::KV_OFF_ST;  // NS stages of [64 lse2 | 64 scale D]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X::KV_OFF_BAR);
   uint64_t* bar_kv = bars + 0;      // K, V landed
   uint64_t* st_full = bars + 1;     // S^T_i, dP^T_i in TMEM
@@ -404,17 +407,19 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
       mbar_arrive_expect_tx(bar_kv, 2 * TA::BYTES);
       tma_load_tile<DH, 128>(sK, &mk128, &mk32, bar_kv, k0, h, b);
       tma_load_tile<DH, 128>(sV, &mv128, &mv32, bar_kv, k0, h, b);
-      for (int i = 0; i < NS && i < T_tiles; ++i) {
-        mbar_arrive_expect_tx(bar_q + i, 2 * TB::BYTES);
-        tma_load_tile<DH, kBT>(sQ + i * TB::BYTES, &mq128, &mq32, bar_q + i, i * kBT, h, b);
-        tma_load_tile<DH, kBT>(sDO + i * TB::BYTES, &mdo128, &mdo32, bar_q + i, i * kBT, h, b);
-      }
+      const float* lse_bh = prm.lse2 + ((int64_t)b * prm.H + h) * prm.Npad;
+      const float* dsc_bh = prm.dsc + ((int64_t)b * prm.H + h) * prm.Npad;
+      auto load_stage = [&](int st, int tile) {
+        mbar_arrive_expect_tx(bar_q + st, 2 * TB::BYTES + 512);
+        tma_load_tile<DH, kBT>(sQ + st * TB::BYTES, &mq128, &mq32, bar_q + st, tile * kBT, h, b);
+        tma_load_tile<DH, kBT>(sDO + st * TB::BYTES, &mdo128, &mdo32, bar_q + st, tile * kBT, h, b);
+        bulk_g2s(sST + st * 512, lse_bh + tile * kBT, 256, bar_q + st);
+        bulk_g2s(sST + st * 512 + 256, dsc_bh + tile * kBT, 256, bar_q + st);
+      };
+      for (int i = 0; i < NS && i < T_tiles; ++i) load_stage(i, i);
       for (int i = 0; i + NS < T_tiles; ++i) {
-        const int st = i % NS;
-        mbar_wait(dkv_done, i & 1);  // Q_i / dO_i consumed
-        mbar_arrive_expect_tx(bar_q + st, 2 * TB::BYTES);
-        tma_load_tile<DH, kBT>(sQ + st * TB::BYTES, &mq128, &mq32, bar_q + st, (i + NS) * kBT, h, b);
-        tma_load_tile<DH, kBT>(sDO + st * TB::BYTES, &mdo128, &mdo32, bar_q + st, (i + NS) * kBT, h, b);
+        mbar_wait(dkv_done, i & 1);  // Q_i / dO_i (and the statistics of tile i) consumed
+        load_stage(i % NS, i + NS);
       }
     }
   } else if (warp == kBMmaWarp) {
@@ -465,12 +470,15 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
     }
     const int row = k0 + r;
     const float c = prm.scale_log2e, sc = prm.scale;
-    // per-QUERY statistics of the streamed tile: identical addresses for every thread of a warp (broadcast loads), 16-byte
-    // vectors; the arrays are padded to a multiple of 64 tokens with zeros
-    const float4* l4 = reinterpret_cast<const float4*>(prm.lse2 + ((int64_t)b * prm.H + h) * prm.Npad) + hh * 8;
-    const float4* d4 = reinterpret_cast<const float4*>(prm.dsc + ((int64_t)b * prm.H + h) * prm.Npad) + hh * 8;
+    // per-QUERY statistics of the streamed tile: staged in shared memory by the TMA warp (global loads here sat on the
+    // critical path of every tile: an L2 round trip after each wake-up); identical addresses for every thread of a warp
+    // (broadcast 16-byte loads); the arrays are padded to a multiple of 64 tokens with zeros
     for (int i = 0; i < T_tiles; ++i) {
       const uint32_t ph = i & 1;
+      const int st = i % NS;
+      const float4* l4 = reinterpret_cast<const float4*>(sST + st * 512) + hh * 8;
+      const float4* d4 = l4 + 16;
+      mbar_wait(bar_q + st, (i / NS) & 1);  // completed before S^T_i was issued: orders the bulk-copied statistics
       mbar_wait(st_full, ph);
       tc_fence_after();
       uint32_t s[32], dp[32];
@@ -479,7 +487,7 @@ spatial_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mk128, const __g
       tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 8; ++g) {  // 4 queries per step
-        const float4 lq = __ldg(l4 + i * 16 + g), dq4 = __ldg(d4 + i * 16 + g);
+        const float4 lq = l4[g], dq4 = d4[g];
         const float p0 = ex2_approx(fmaf(__uint_as_float(s[4 * g + 0]), c, -lq.x));
         const float p1 = ex2_approx(fmaf(__uint_as_float(s[4 * g + 1]), c, -lq.y));
         const float p2 = ex2_approx(fmaf(__uint_as_float(s[4 * g + 2]), c, -lq.z));
