@@ -18,97 +18,125 @@ union Vec8 {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// LayerNorm over the last dim C (multiple of 8, <= 2048): one warp per row, two-pass statistics in registers
+// LayerNorm over the last dim C (multiple of 8, <= 2048). Rows are contiguous, so a tile of TR consecutive rows is ONE
+// 1-D bulk copy (TMA engine) into shared memory and one bulk store back: the bytes in flight per SM are set by the tile
+// size and the number of resident CTAs (2 stages x ~20 KB x up to 5 CTAs), not by how many registers a warp can keep
+// loaded - the register-only version of this kernel held 24 warps x 1.3 KB = 30 KB per SM in flight at C = 320 (80
+// registers per thread) and measured 0.36-0.43 of the HBM peak. One warp per row, two-pass statistics in fp32 in the same
+// summation order as before (per-lane sums, then the xor butterfly); the result overwrites the row in its stage.
 // ---------------------------------------------------------------------------------------------------------------
 template <int VPL>  // vectors (of 8 halfs) per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                         const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                                         const __half* __restrict__ post_add,
                                                         const __half* __restrict__ pre_bias, int rows_per_frame, int frames,
-                                                        int64_t rows, int C, float eps) {
-  constexpr int R = 2;  // rows per warp and trip: both rows' loads are issued before either reduction starts
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                                                        int64_t rows, int C, float eps, int TR, int64_t n_tiles) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const uint32_t stage_bytes = (uint32_t)TR * C * 2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + 2 * stage_bytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = C / 8;
-  for (int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * R; row0 < rows; row0 += (int64_t)gridDim.x * 8 * R) {
-    Vec8 a[R][VPL];
-    float s[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      s[r] = 0.f;
-      const bool live = row0 + r < rows;
-      const __half* xr = x + (row0 + r) * C;
+  if (tid == 0) {
+    mbar_init(bars, 1), mbar_init(bars + 1, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto tile_bytes = [&](int64_t t) {
+    const int64_t r = rows - t * TR;
+    return (uint32_t)((r < TR ? r : TR) * C * 2);
+  };
+  auto load_tile = [&](int64_t t, int st) {
+    mbar_arrive_expect_tx(bars + st, tile_bytes(t));
+    bulk_g2s(ln_smem + st * stage_bytes, x + t * TR * C, tile_bytes(t), bars + st);
+  };
+  // gamma, beta and the folded residual bias: staged once per CTA behind the two stages (3 x C halfs)
+  __half* s_par = reinterpret_cast<__half*>(ln_smem + 2 * stage_bytes + 16);
+  for (int v = tid; v < V; v += 256) {
+    reinterpret_cast<uint4*>(s_par)[v] = *reinterpret_cast<const uint4*>(gamma + v * 8);
+    reinterpret_cast<uint4*>(s_par + C)[v] = *reinterpret_cast<const uint4*>(beta + v * 8);
+    reinterpret_cast<uint4*>(s_par + 2 * C)[v] =
+        pre_bias ? *reinterpret_cast<const uint4*>(pre_bias + v * 8) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  int64_t tile = blockIdx.x;
+  if (tid == 0 && tile < n_tiles) load_tile(tile, 0);
+  for (int k = 0; tile < n_tiles; tile += gridDim.x, ++k) {
+    const int st = k & 1;
+    if (tid == 0 && tile + gridDim.x < n_tiles) {
+      bulk_wait_read_all();  // the store that left the other stage one trip ago has read its bytes
+      load_tile(tile + gridDim.x, st ^ 1);
+    }
+    mbar_wait(bars + st, (k >> 1) & 1);
+    uint8_t* stage = ln_smem + st * stage_bytes;
+    const int64_t row_base = tile * TR;
+    const int live = (int)((rows - row_base) < TR ? (rows - row_base) : TR);
+    for (int r = warp; r < live; r += 8) {
+      __half* xr = reinterpret_cast<__half*>(stage) + (int64_t)r * C;
+      Vec8 a[VPL];
+      float s = 0.f;
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         const int v = lane + i * 32;
-        a[r][i].u = make_uint4(0u, 0u, 0u, 0u);
-        if (live && v < V) {
-          a[r][i].u = *reinterpret_cast<const uint4*>(xr + v * 8);
+        a[i].u = make_uint4(0u, 0u, 0u, 0u);
+        if (v < V) {
+          a[i].u = *reinterpret_cast<const uint4*>(xr + v * 8);
           if (pre_bias) {  // x + pre_bias[c] (fp16, as a separate elementwise add would round it) is what gets normalised
             Vec8 pb;
-            pb.u = *reinterpret_cast<const uint4*>(pre_bias + v * 8);
+            pb.u = reinterpret_cast<const uint4*>(s_par + 2 * C)[v];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) a[r][i].h2[j] = __hadd2(a[r][i].h2[j], pb.h2[j]);
+            for (int j = 0; j < 4; ++j) a[i].h2[j] = __hadd2(a[i].h2[j], pb.h2[j]);
           }
         }
       }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int i = 0; i < VPL; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s[r] += __half2float(a[r][i].h[j]);  // padding vectors are zeros
+        for (int j = 0; j < 8; ++j) s += __half2float(a[i].h[j]);  // padding vectors are zeros
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-      for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], off);
-    float mean[R], q[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      mean[r] = s[r] / (float)C;
-      q[r] = 0.f;
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      const float mean = s / (float)C;
+      float q = 0.f;
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
-        const int v = lane + i * 32;
-        if (v < V) {
+        if (lane + i * 32 < V) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float d = __half2float(a[r][i].h[j]) - mean[r];
-            q[r] += d * d;
+            const float d = __half2float(a[i].h[j]) - mean;
+            q += d * d;
           }
         }
       }
-    }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-      for (int r = 0; r < R; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], off);
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int64_t row = row0 + r;
-      if (row >= rows) break;
-      const float rstd = rsqrtf(q[r] / (float)C + eps);
-      __half* yr = y + row * C;
+      for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+      const float rstd = rsqrtf(q / (float)C + eps);
+      const int64_t row = row_base + r;
       const __half* pa = post_add ? post_add + (int64_t)((row / rows_per_frame) % frames) * C : nullptr;
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         const int v = lane + i * 32;
         if (v < V) {
-          Vec8 w, b, o, pe;
-          w.u = *reinterpret_cast<const uint4*>(gamma + v * 8);
-          b.u = *reinterpret_cast<const uint4*>(beta + v * 8);
+          Vec8 o, pe, w, bt;
+          w.u = reinterpret_cast<const uint4*>(s_par)[v];
+          bt.u = reinterpret_cast<const uint4*>(s_par + C)[v];
           if (pa) pe.u = *reinterpret_cast<const uint4*>(pa + v * 8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float f = (__half2float(a[r][i].h[j]) - mean[r]) * rstd * __half2float(w.h[j]) + __half2float(b.h[j]);
+            float f = (__half2float(a[i].h[j]) - mean) * rstd * __half2float(w.h[j]) + __half2float(bt.h[j]);
             if (pa) f = round_half(f) + __half2float(pe.h[j]);  // eager: LayerNorm output (fp16) + pe (fp16)
             o.h[j] = __float2half_rn(f);
           }
-          *reinterpret_cast<uint4*>(yr + v * 8) = o.u;
+          *reinterpret_cast<uint4*>(xr + v * 8) = o.u;
         }
       }
     }
+    fence_proxy_async();  // the rows written above -> visible to the bulk-store engine
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(y + row_base * C, stage, tile_bytes(tile));
+      bulk_commit();
+    }
   }
+  if (tid == 0) bulk_wait_read_all();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -217,14 +245,29 @@ extern "C" int mc_layernorm(const void* x, void* y, const void* gamma, const voi
     set_error("layernorm: post_add needs rows_per_frame > 0 and frames > 0");
     return MC_E_INVALID;
   }
-  int64_t blocks = (rows + 15) / 16;  // 8 warps x 2 rows per CTA and trip
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)post_add | (uintptr_t)pre_bias) % 16) {
+    set_error("layernorm: pointers must be 16-byte aligned");
+    return MC_E_INVALID;
+  }
+  // rows per tile: ~20 KB stages (C = 320 -> 32 rows, 640 -> 16, 1280 -> 8), at most 4 rows per warp
+  int rw = 20480 / (C * 2 * 8);
+  rw = rw < 1 ? 1 : (rw > 4 ? 4 : rw);
+  const int TR = 8 * rw;
+  const int64_t n_tiles = (rows + TR - 1) / TR;
+  const size_t smem = 2 * (size_t)TR * C * 2 + 16 + 3 * (size_t)C * 2;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  per_sm = per_sm > 8 ? 8 : per_sm;
+  int64_t blocks = n_tiles < (int64_t)148 * per_sm ? n_tiles : (int64_t)148 * per_sm;
   cudaStream_t st = (cudaStream_t)stream;
   const int vpl = (C / 8 + 31) / 32;
-#define MC_LN(V)                                                                                                \
-  layernorm_kernel<V><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, (__half*)y, (const __half*)gamma,     \
-                                                        (const __half*)beta, (const __half*)post_add,                 \
-                                                        (const __half*)pre_bias, rows_per_frame, frames, rows, C, eps)
+#define MC_LN(V)                                                                                                   \
+  do {                                                                                                             \
+    cudaFuncSetAttribute(layernorm_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+    layernorm_kernel<V><<<(unsigned)blocks, 256, smem, st>>>((const __half*)x, (__half*)y, (const __half*)gamma,   \
+                                                             (const __half*)beta, (const __half*)post_add,        \
+                                                             (const __half*)pre_bias, rows_per_frame, frames, rows, C, \
+                                                             eps, TR, n_tiles);                                    \
+  } while (0)
   switch (vpl) {
     case 1: MC_LN(1); break;
     case 2: MC_LN(2); break;

@@ -6,23 +6,24 @@
 // N = h*w tokens of one frame; N = 4096 / 1024 / 256 / 64 and DH = 40 / 80 / 160 / 160 at 16 x 512 x 512. fp32 softmax
 // statistics, one rounding of the output (xformers / flash semantics - SURVEY.md appendix "Attention numerics").
 //
-// Forward, one CTA = one (frame, head, 128-query tile); 160 threads = 4 softmax warps (thread r owns query row r = TMEM
-// lane r) + 1 producer warp whose lane 0 issues every TMA load and every MMA. Per BN-key tile j (BN = 64 for head dims
-// <= 48, where four CTAs share an SM - 16 softmax warps - and 128 otherwise, two CTAs per SM):
-//   producer:  S = Q K_j^T           tcgen05.mma M=128 N=BN K=DH, A/B from shared memory -> TMEM [0,BN)   -> commit s_full
-//   softmax :  S -> registers (BN fp32 per thread), row max, exp2, P -> fp16 pairs -> tcgen05.st back into TMEM columns
-//              [0, BN/2) of the thread's own lane (over its own, already consumed, S)                      -> arrive p_full
-//   producer:  O += P V_j, L += P 1  tcgen05.mma with the A operand (P) read FROM TENSOR MEMORY, B = V_j MN-major straight
-//              from its TMA tile (no transpose) / a tile of ones; then S_{j+1}                             -> commit pv_done
-// P never touches shared memory: the only shared-memory traffic is TMA writes and the MMA's operand reads (the first
-// version staged P through 32 KB of shared memory per tile and was co-limited by the 128 B/cycle shared-memory port).
-// The tensor pipe executes in issue order, so P V_j (reads P) may be followed at once by S_{j+1} (overwrites it).
-// The kernel is bound by the exponentials (16 / cycle / SM; a 128 x 128 x 48 MMA pair is ~400 cycles), so instructions are
-// taken out of the softmax warps wherever possible: the row sum is accumulated by the tensor core as 16 extra accumulator
-// columns L = P x ones, from the same fp16 P the numerator uses. O and L stay in TMEM for the whole key loop; the running
-// maximum is only raised when a row's maximum grows by more than 2^8 (P <= 256 fits fp16; exactness is unaffected because
-// numerator and denominator share the reference maximum); only then does the softmax warp rescale its 32 rows of O | L
-// (tcgen05.ld -> multiply -> tcgen05.st). K and V tiles are double-buffered TMA loads.
+// Forward, one CTA = one (frame, head, 128-query tile); 192 threads = 4 softmax warps (thread r owns query row r = TMEM
+// lane r) + 1 MMA warp (lane 0 issues every tcgen05.mma) + 1 load warp (lane 0 issues every TMA load). Key tiles of 64;
+// the score tile S is DOUBLE-BUFFERED in tensor memory so that the tensor pipe computes S_{j+1} while the softmax warps
+// are still working on S_j (S_{j+1} = Q K_{j+1}^T does not depend on them):
+//   MMA warp:  S_{j+1} = Q K_{j+1}^T   tcgen05.mma M=128 N=64 K=DH, A/B from shared memory -> TMEM buffer (j+1)&1  -> commit s_full[(j+1)&1]
+//   softmax :  S_j -> registers (64 fp32 per thread), row max, exp2, P_j -> fp16 pairs -> tcgen05.st back over the first 32
+//              columns of the thread's own lane in buffer j&1 (its own, already consumed, S_j)                    -> arrive p_full[j&1]
+//   MMA warp:  O += P_j V_j            tcgen05.mma with the A operand (P) read FROM TENSOR MEMORY, B = V_j MN-major straight
+//              from its TMA tile (no transpose)                                           -> commit pv_done, stage_free[j % NS]
+// Pipe order S0 S1 PV0 S2 PV1 S3 ...: the tensor pipe executes in issue order, so S_{j+2} (which overwrites buffer j&1) is
+// behind P V_j (which reads P_j from it). Round-2 ncu of the single-buffered version: the softmax warps spent 35 % of their
+// time parked on s_full - S_{j+1} could only be issued behind P V_j, i.e. after the slowest of the four warps had finished
+// tile j - and moving half of the exponentials to the FMA pipe changed nothing: the kernel was bound by that serial
+// chain, not by MUFU throughput.
+// P never touches shared memory: the only shared-memory traffic is TMA writes and the MMA's operand reads. O stays in TMEM
+// for the whole key loop; the running maximum is only raised when a row's maximum grows by more than 2^8 (P <= 256 fits
+// fp16; exactness is unaffected because numerator and denominator share the reference maximum); only then does the softmax
+// warp rescale its 32 rows of O (tcgen05.ld -> multiply -> tcgen05.st). K and V tiles stream through an NS-stage TMA ring.
 #include <math.h>
 
 #include "tma_common.cuh"
@@ -30,7 +31,9 @@
 namespace mc {
 
 constexpr int kFM = 128;         // query rows per CTA (UMMA M)
-constexpr int kFThreads = 160;   // 4 softmax warps + 1 producer warp
+constexpr int kFBN = 64;         // keys per tile (UMMA N of S, K extent of P V)
+constexpr int kFThreads = 192;   // 4 softmax warps + MMA warp + load warp
+constexpr int kFMmaWarp = 4, kFTmaWarp = 5;
 constexpr float kRescaleThreshold = 8.f;  // log2 units
 
 struct FAParams {
@@ -45,18 +48,19 @@ template <int DH>
 struct FACfg {
   using T = TileParts<DH>;            // Q tile (128 rows)
   static constexpr int DHP = T::DHP;
-  static constexpr int BN = DHP <= 48 ? 64 : 128;   // keys per tile (UMMA N of S, K extent of P V)
+  static constexpr int BN = kFBN;
   using TK = TileParts<DH, BN>;       // K / V tiles
   // Row sums: when the head dim leaves zero-padded columns in the V tile (DH = 40 -> 48), column DH of V is set to 1.0
   // after every TMA load, so accumulator column DH of O = P V IS the row sum (from the same fp16 P as the numerator, at no
   // extra MMA and no extra instruction in the softmax warps). Otherwise the softmax threads add their probabilities.
   static constexpr bool PAD_SUM = DHP > DH && DH < 64;
-  static constexpr int OFF_Q = 0, OFF_K = T::BYTES, OFF_V = OFF_K + 2 * TK::BYTES;   // K, V: 2 stages each
-  static constexpr int OFF_BAR = OFF_V + 2 * TK::BYTES;
-  static constexpr int SMEM = OFF_BAR + 128 + 1024;          // + alignment slack (dynamic smem base is 16 B aligned)
-  static constexpr int O_COL = BN;                           // S / P at TMEM [0, BN), O at [BN, BN + DHP)
+  static constexpr int NS = DHP <= 80 ? 4 : 3;               // K / V ring depth
+  static constexpr int OFF_Q = 0, OFF_K = T::BYTES, OFF_V = OFF_K + NS * TK::BYTES;
+  static constexpr int OFF_BAR = OFF_V + NS * TK::BYTES;
+  static constexpr int SMEM = OFF_BAR + 256 + 1024;          // + alignment slack (dynamic smem base is 16 B aligned)
+  static constexpr int O_COL = 2 * BN;                       // S / P buffers at TMEM [0, BN), [BN, 2 BN); O at [2 BN, 2 BN + DHP)
   static constexpr int ACC_COLS = DHP;
-  static constexpr int TCOLS = (BN + ACC_COLS <= 128) ? 128 : ((BN + ACC_COLS <= 256) ? 256 : 512);
+  static constexpr int TCOLS = (O_COL + ACC_COLS <= 256) ? 256 : 512;
   static constexpr int CTAS_TMEM = 512 / TCOLS, CTAS_SMEM = (227 * 1024) / SMEM;
   static constexpr int CTAS_PER_SM = CTAS_TMEM < CTAS_SMEM ? CTAS_TMEM : (CTAS_SMEM < 1 ? 1 : CTAS_SMEM);
 };
@@ -102,7 +106,7 @@ __device__ __forceinline__ void issue_pv(uint32_t o_tmem, uint32_t p_tmem, uint3
   }
 }
 
-// all lanes of the producer warp: element DH of every key row of a landed V tile := 1.0 (see FACfg::PAD_SUM)
+// all lanes of the load warp: element DH of every key row of a landed V tile := 1.0 (see FACfg::PAD_SUM)
 template <int DH>
 __device__ __forceinline__ void write_v_ones(uint8_t* sVstage, int lane) {
   using X = FACfg<DH>;
@@ -122,31 +126,34 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
   using X = FACfg<DH>;
   using T = TileParts<DH>;
   using TK = typename X::TK;
-  constexpr int DHP = X::DHP, BN = X::BN;
+  constexpr int DHP = X::DHP, BN = X::BN, NS = X::NS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem + X::OFF_Q;
-  uint8_t* sK = smem + X::OFF_K;   // 2 stages
-  uint8_t* sV = smem + X::OFF_V;   // 2 stages
+  uint8_t* sK = smem + X::OFF_K;   // NS stages
+  uint8_t* sV = smem + X::OFF_V;   // NS stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X::OFF_BAR);
-  uint64_t* bar_q = bars + 0;      // Q landed                         (tx)
-  uint64_t* bar_kv = bars + 1;     // [2] K_j and V_j landed in stage j & 1 (tx)
-  uint64_t* s_full = bars + 3;     // S_j in TMEM                      (tcgen05.commit)
-  uint64_t* p_full = bars + 4;     // P_j in TMEM, S_j consumed        (4 warp arrivals)
-  uint64_t* pv_done = bars + 5;    // O += P_j V_j completed           (tcgen05.commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_q = bars + 0;        // Q landed                                         (tx)
+  uint64_t* s_full = bars + 1;       // [2] S_j in TMEM buffer j & 1                      (tcgen05.commit)
+  uint64_t* p_full = bars + 3;       // [2] P_j in TMEM buffer j & 1, S_j consumed        (4 warp arrivals)
+  uint64_t* pv_done = bars + 5;      // O += P_j V_j completed                            (tcgen05.commit)
+  uint64_t* kv_full = bars + 6;      // [NS] K_j and V_j landed in stage j % NS            (tx)
+  uint64_t* v_ready = bars + 10;     // [NS] ones column written into V_j (PAD_SUM)        (1 arrival)
+  uint64_t* stage_free = bars + 14;  // [NS] S_j and P V_j completed: stage j % NS may be refilled (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * kFM, N = prm.N;
   const int T_tiles = (N + BN - 1) / BN;
 
-  if (warp == 4) {
+  if (warp == kFMmaWarp) {
     tmem_alloc<X::TCOLS>(tmem_slot);
     if (lane == 0) {
-      mbar_init(bar_q, 1), mbar_init(bar_kv, 1), mbar_init(bar_kv + 1, 1), mbar_init(s_full, 1);
-      mbar_init(p_full, 4), mbar_init(pv_done, 1);
+      mbar_init(bar_q, 1), mbar_init(pv_done, 1);
+      for (int i = 0; i < 2; ++i) mbar_init(s_full + i, 1), mbar_init(p_full + i, 4);
+      for (int i = 0; i < NS; ++i) mbar_init(kv_full + i, 1), mbar_init(v_ready + i, 1), mbar_init(stage_free + i, 1);
       fence_mbar_init();
       tma_prefetch_desc(&mq128), tma_prefetch_desc(&mk128), tma_prefetch_desc(&mv128);
     }
@@ -156,52 +163,56 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
-    // ================= producer warp: lane 0 issues every TMA load and MMA =================
+  if (warp == kFTmaWarp) {
+    // ================= load warp: lane 0 issues every TMA load; all lanes write the ones column =================
+    auto load_kv = [&](int j) {
+      const int st = j % NS;
+      mbar_arrive_expect_tx(kv_full + st, 2 * TK::BYTES);
+      tma_load_tile<DH, BN>(sK + st * TK::BYTES, &mk128, &mk32, kv_full + st, j * BN, h, b);
+      tma_load_tile<DH, BN>(sV + st * TK::BYTES, &mv128, &mv32, kv_full + st, j * BN, h, b);
+    };
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_q, T::BYTES);
       tma_load_tile<DH>(sQ, &mq128, &mq32, bar_q, q0, h, b);
-      for (int j = 0; j < 2 && j < T_tiles; ++j) {
-        mbar_arrive_expect_tx(bar_kv + j, 2 * TK::BYTES);
-        tma_load_tile<DH, BN>(sK + j * TK::BYTES, &mk128, &mk32, bar_kv + j, j * BN, h, b);
-        tma_load_tile<DH, BN>(sV + j * TK::BYTES, &mv128, &mv32, bar_kv + j, j * BN, h, b);
-      }
+      for (int j = 0; j < NS && j < T_tiles; ++j) load_kv(j);
     }
-    mbar_wait(bar_q, 0);
-    mbar_wait(bar_kv, 0);
-    if constexpr (X::PAD_SUM) write_v_ones<DH>(sV, lane);
+    for (int j = 0; j < T_tiles; ++j) {
+      if constexpr (X::PAD_SUM) {
+        const int st = j % NS;
+        mbar_wait(kv_full + st, (j / NS) & 1);
+        write_v_ones<DH>(sV + st * TK::BYTES, lane);
+        if (lane == 0) mbar_arrive(v_ready + st);
+      }
+      if (j >= 1 && j - 1 + NS < T_tiles) {  // refill the stage of tile j - 1 once its MMAs have completed
+        mbar_wait(stage_free + (j - 1) % NS, ((j - 1) / NS) & 1);
+        if (lane == 0) load_kv(j - 1 + NS);
+      }
+      __syncwarp();
+    }
+  } else if (warp == kFMmaWarp) {
+    // ================= MMA warp: lane 0 issues every MMA =================
     if (lane == 0) {
+      mbar_wait(bar_q, 0);
+      mbar_wait(kv_full, 0);
       tc_fence_after();
       issue_qk<DH>(tmem_base, smem_u32(sQ), smem_u32(sK));
       umma_commit(s_full);
-    }
-    for (int j = 0; j < T_tiles; ++j) {
-      const uint32_t ph = j & 1, st = j & 1;
-      mbar_wait(p_full, ph);  // every softmax thread has consumed S_j and written P_j
-      if (lane == 0) {
-        tc_fence_after();
-        issue_pv<DH>(tmem_base + X::O_COL, tmem_base, smem_u32(sV + st * TK::BYTES), j > 0);
-        umma_commit(pv_done);
-      }
-      if (j + 1 < T_tiles) {  // S_{j+1} right behind P V_j (in-order pipe: P_j is read before it is overwritten)
-        const int sn = (j + 1) & 1;
-        mbar_wait(bar_kv + sn, ((j + 1) >> 1) & 1);
-        if constexpr (X::PAD_SUM) write_v_ones<DH>(sV + sn * TK::BYTES, lane);
-        if (lane == 0) {
+      for (int j = 0; j < T_tiles; ++j) {
+        const int st = j % NS, buf = j & 1;
+        if (j + 1 < T_tiles) {  // S_{j+1} into the other buffer while the softmax warps work on S_j
+          const int sn = (j + 1) % NS;
+          mbar_wait(kv_full + sn, ((j + 1) / NS) & 1);
           tc_fence_after();
-          issue_qk<DH>(tmem_base, smem_u32(sQ), smem_u32(sK + sn * TK::BYTES));
-          umma_commit(s_full);
+          issue_qk<DH>(tmem_base + (buf ^ 1) * BN, smem_u32(sQ), smem_u32(sK + sn * TK::BYTES));
+          umma_commit(s_full + (buf ^ 1));
         }
+        mbar_wait(p_full + buf, (j >> 1) & 1);  // every softmax thread has consumed S_j and written P_j
+        if constexpr (X::PAD_SUM) mbar_wait(v_ready + st, (j / NS) & 1);
+        tc_fence_after();
+        issue_pv<DH>(tmem_base + X::O_COL, tmem_base + buf * BN, smem_u32(sV + st * TK::BYTES), j > 0);
+        umma_commit(pv_done);
+        umma_commit(stage_free + st);
       }
-      if (j + 2 < T_tiles) {
-        mbar_wait(pv_done, ph);  // K_j / V_j consumed: refill the stage with tile j + 2
-        if (lane == 0) {
-          mbar_arrive_expect_tx(bar_kv + st, 2 * TK::BYTES);
-          tma_load_tile<DH, BN>(sK + st * TK::BYTES, &mk128, &mk32, bar_kv + st, (j + 2) * BN, h, b);
-          tma_load_tile<DH, BN>(sV + st * TK::BYTES, &mv128, &mv32, bar_kv + st, (j + 2) * BN, h, b);
-        }
-      }
-      __syncwarp();
     }
   } else {
     // ================= softmax warps: thread = query row =================
@@ -210,11 +221,12 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
     float m_used = -INFINITY, l_thr = 0.f;  // l_thr: thread-side row sum (unused when the V pad column carries it)
     for (int j = 0; j < T_tiles; ++j) {
       const uint32_t ph = j & 1;
-      mbar_wait(s_full, ph);
+      const uint32_t sbuf = lane_addr + (j & 1) * BN;
+      mbar_wait(s_full + (j & 1), (j >> 1) & 1);
       tc_fence_after();
       uint32_t s[BN];
 #pragma unroll
-      for (int cc = 0; cc < BN / 32; ++cc) tmem_ld32(lane_addr + cc * 32, s + cc * 32);
+      for (int cc = 0; cc < BN / 32; ++cc) tmem_ld32(sbuf + cc * 32, s + cc * 32);
       tmem_ld_wait();
 
       const int kvalid = N - j * BN;  // keys of this tile that exist (>= 1)
@@ -240,7 +252,7 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
           const float alpha = ex2_approx(m_used - m_new);
           m_used = m_new;
           l_thr *= alpha;
-          mbar_wait(pv_done, ph ^ 1);  // O holds tiles 0..j-1
+          mbar_wait(pv_done, ph ^ 1);  // O holds tiles 0..j-1 (P V_j cannot start before this warp's p_full arrival)
           tc_fence_after();
 #pragma unroll
           for (int cc = 0; cc < X::ACC_COLS / 16; ++cc) {
@@ -264,14 +276,16 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
         s[i >> 1] = pack_half2(p0, p1);
       }
       if constexpr (!X::PAD_SUM) l_thr += l0 + l1;
-#pragma unroll
-      for (int cc = 0; cc < BN / 64; ++cc) tmem_st32(lane_addr + cc * 32, s + cc * 32);  // P over the consumed S
+      tmem_st32(sbuf, s);  // P over the consumed S (first BN / 2 columns of the buffer)
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(p_full + (j & 1));
     }
     // ---- epilogue: O / l -> fp16 -> global; log-sum-exp for the backward ----
+    // S_{T-1} was issued BEFORE P V_{T-2}, so having consumed it only proves P V_{T-3} complete: a single parity wait for
+    // phase T-1 could be satisfied by the still-incomplete phase T-2 looking like "phase T-3 done". Wait for both in order.
+    if (T_tiles >= 2) mbar_wait(pv_done, (T_tiles - 2) & 1);
     mbar_wait(pv_done, (T_tiles - 1) & 1);
     tc_fence_after();
     const int row = q0 + tid;
@@ -308,7 +322,7 @@ spatial_attn_fwd_kernel(const __grid_constant__ CUtensorMap mq128, const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kFMmaWarp) {
     __syncwarp();
     tmem_dealloc<X::TCOLS>(tmem_base);
   }

@@ -60,7 +60,15 @@ def linear_into_residual(x, linear: nn.Linear, residual):
     """residual + x @ W^T as ONE GEMM (beta = 1 epilogue) - the projection's bias is NOT added here: the caller carries it
     inside the residual stream (fold_residual_biases)."""
     c_out = linear.out_features
-    return torch.addmm(residual.reshape(-1, c_out), x.reshape(-1, x.shape[-1]), linear.weight.t()).view(residual.shape)
+    r2, x2 = residual.reshape(-1, c_out), x.reshape(-1, x.shape[-1])
+    if not torch.is_grad_enabled() or not (residual.requires_grad or x.requires_grad):
+        # no-grad forwards (plain steps, the unconditional half of guided steps): accumulate INTO the residual stream.
+        # Out of place, ATen first copies `residual` into the result (a memcpy of the whole activation per projection:
+        # 108 per UNet forward, 3 % of a plain step in the round-2 profile) and then runs the same beta = 1 GEMM on it, so
+        # the values are identical. The stream tensor is owned by the transformer (the output of its proj_in GEMM) and
+        # its previous value is dead after this add.
+        return r2.addmm_(x2, linear.weight.t()).view(residual.shape)
+    return torch.addmm(r2, x2, linear.weight.t()).view(residual.shape)
 
 
 def fold_residual_biases(biases):
