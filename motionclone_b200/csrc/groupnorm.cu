@@ -112,9 +112,9 @@ __global__ void __launch_bounds__(512, 2) groupnorm_stats_kernel(const __half* _
     gn_fetch(buf + (t & 1) * stage_bytes, x, n, HW, C, p0, npx, bar + (t & 1));
   };
   if (tid == 0 && ntrips > 0) fetch(0);
-  float sum[8], sq[8];
+  uint64_t sum2[4], sq2[4];  // channel pairs (2j, 2j + 1): FADD2 / FFMA2, bit-identical to eight scalar accumulators
 #pragma unroll
-  for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+  for (int j = 0; j < 4; ++j) sum2[j] = sq2[j] = f2_pack(0.f, 0.f);
   const bool has_cb = chan_bias != nullptr;
   GVec8 cb;
   cb.u = make_uint4(0u, 0u, 0u, 0u);
@@ -130,15 +130,25 @@ __global__ void __launch_bounds__(512, 2) groupnorm_stats_kernel(const __half* _
         GVec8 a;
         a.u = *reinterpret_cast<const uint4*>(tile + ((int64_t)pp * C + v * 8) * 2);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float f = __half2float(a.h[j]);
-          if (has_cb) f = round_half(f + __half2float(cb.h[j]));  // the eager `h + temb` is an fp16 tensor
-          sum[j] += f;
-          sq[j] = fmaf(f, f, sq[j]);
+        for (int j = 0; j < 4; ++j) {
+          float f0 = __half2float(a.h[2 * j]), f1 = __half2float(a.h[2 * j + 1]);
+          if (has_cb) {  // the eager `h + temb` is an fp16 tensor
+            f0 = round_half(f0 + __half2float(cb.h[2 * j]));
+            f1 = round_half(f1 + __half2float(cb.h[2 * j + 1]));
+          }
+          const uint64_t f = f2_pack(f0, f1);
+          sum2[j] = f2_add(sum2[j], f);
+          sq2[j] = f2_fma(f, f, sq2[j]);
         }
       }
     }
     if (t + 1 < ntrips) __syncthreads();  // every thread is done with this stage
+  }
+  float sum[8], sq[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f2_unpack(sum2[j], sum[2 * j], sum[2 * j + 1]);
+    f2_unpack(sq2[j], sq[2 * j], sq[2 * j + 1]);
   }
   __syncthreads();  // the tile is dead: its shared memory becomes the reduction slots
 #pragma unroll

@@ -76,6 +76,28 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // generic-proxy smem writes -> visible to the async proxy (bulk store engine)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- packed fp32 pairs (sm_100: FADD2 / FFMA2 issue two IEEE fp32 operations per lane and instruction) ----
+// Each half of a pair is an ordinary round-to-nearest fp32 operation: results are bit-identical to the scalar code, the
+// issue count halves (the GroupNorm statistics pass is bound by instruction issue, not by HBM).
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 // ---- ldmatrix ----
 __device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
