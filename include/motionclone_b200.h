@@ -114,7 +114,7 @@ int mc_add_noise(const void* x0, const void* noise, void* out, int64_t n, float 
                  void* stream);
 
 /*
- * Text cross-attention forward on tcgen05 tensor cores with TMEM accumulators (csrc/cross_attn_tc.cu):
+ * Text cross-attention forward on tcgen05 tensor cores with TMEM accumulators (csrc/cross_attn_fwd_tc.cu):
  * O = softmax(scale * Q K^T) V per (batch, head), Q [B, Nq, H*DH] (all frames of one prompt), K, V [B, Nk <= 80, H*DH].
  * Replaces the xformers call for `attn2` (models/attention.py:193-201, :280-285 -> :535-542).
  * Strides in elements (multiples of 8); head h occupies columns [h*DH, (h+1)*DH). DH in {16, 32, 40, 64, 80, 160}.
@@ -124,7 +124,7 @@ int mc_cross_attn_fwd(const void* q, const void* k, const void* v, void* o, int 
                       int64_t o_stride_b, int64_t o_stride_row, float scale, void* stream);
 
 /*
- * Gradient of the same cross-attention with respect to Q only (tcgen05, csrc/cross_attn_tc.cu):
+ * Gradient of the same cross-attention with respect to Q only (tcgen05, csrc/cross_attn_bwd_tc.cu):
  * dQ = scale * [P o (dO V^T - rowsum(P o dO V^T))] K with P recomputed from Q, K. The text K / V are projections of a
  * constant prompt embedding through frozen weights (t2v_video_sample.py:67-68), so torch.autograd.grad w.r.t. the
  * latents (utils/motionclone_functions.py:236) never asks for dK / dV; the Python wrapper raises if it is asked to.

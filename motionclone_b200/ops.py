@@ -516,7 +516,7 @@ def _check_xattn(q: Tensor, k: Tensor, v: Tensor) -> None:
 
 
 def cross_attention_forward(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float) -> Tensor:
-    """tcgen05 text cross-attention (csrc/cross_attn_tc.cu): q [B, Nq, C], k / v [B, Nk <= 80, C] -> [B, Nq, C]."""
+    """tcgen05 text cross-attention (csrc/cross_attn_fwd_tc.cu, csrc/cross_attn_bwd_tc.cu): q [B, Nq, C], k / v [B, Nk <= 80, C] -> [B, Nq, C]."""
     _check_xattn(q, k, v)
     B, Nq, C = q.shape
     o = torch.empty((B, Nq, C), dtype=q.dtype, device=q.device)

@@ -9,7 +9,7 @@ Design differences (B200-first):
   checkpoint, `use_linear_projection=False`) run as GEMMs on that view;
 * self-attention projects q,k,v with one GEMM; cross-attention projects the text K/V ONCE per prompt, not once per
   frame (the reference repeats the text f times, attention.py:100, and re-projects it for every frame);
-* text cross-attention (`attn2`) runs on this package's tcgen05 / TMEM kernels (csrc/cross_attn_tc.cu), forward and
+* text cross-attention (`attn2`) runs on this package's tcgen05 / TMEM kernels (csrc/cross_attn_fwd_tc.cu, csrc/cross_attn_bwd_tc.cu), forward and
   the gradient w.r.t. the queries (the text K / V carry no gradient on the MotionClone path);
 * spatial SELF-attention at the reference's xformers seam (`_memory_efficient_attention_xformers`, :535-542) runs on this
   package's tcgen05 + tensor-map TMA flash kernels (csrc/spatial_attn_tc.cu), forward and backward (dQ, dK, dV);
@@ -27,7 +27,7 @@ from torch import nn
 from . import ops
 
 
-_XATTN_TC_HEAD_DIMS = (8, 16, 32, 40, 64, 80, 160)  # instantiations of csrc/cross_attn_tc.cu
+_XATTN_TC_HEAD_DIMS = (8, 16, 32, 40, 64, 80, 160)  # instantiations of csrc/cross_attn_{fwd,bwd}_tc.cu
 
 
 def _need_kernels(x, what: str) -> None:
@@ -289,7 +289,7 @@ class CrossAttention(nn.Module):
             if ctx.shape[1] > 80 or dh not in _XATTN_TC_HEAD_DIMS or (torch.is_grad_enabled() and kv.requires_grad):
                 raise NotImplementedError("text cross-attention kernel: <= 80 context tokens, head dim in "
                                           f"{_XATTN_TC_HEAD_DIMS}, frozen K / V projections of a constant prompt")
-            # tcgen05 / TMEM kernels (csrc/cross_attn_tc.cu); dQ only: the text K / V carry no gradient here
+            # tcgen05 / TMEM kernels (csrc/cross_attn_{fwd,bwd}_tc.cu); dQ only: the text K / V carry no gradient here
             if torch.is_grad_enabled() and q.requires_grad:
                 o = ops.CrossAttentionTC.apply(q, k, v, h, self.scale)
             else:
