@@ -239,7 +239,7 @@ def run_reference_arm(args):
             "arm": f"reference CPU path (oracle port, fp32, {info['cores']} host threads), rank 0 only",
             "cpu_baseline": cpu_block(tg, tp, info, infer, fps),
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -485,7 +485,19 @@ def run_own_arm(args):
                     "h2d_bytes_per_step": lat_bytes + text_host[0].numel() * 2 + rep_host.numel(),
                     "d2h_bytes_per_step": lat_bytes, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "gpu_reference": gpu_ref, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_RESULT_FD = None
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -503,6 +515,13 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=240.0, help="seconds of CPU work for --impl reference")
     ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work for the cpu_baseline leg")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner on the first
+    # communicator when NCCL_DEBUG=VERSION is set in the environment), so everything but the result goes to stderr: file
+    # descriptor 1 is pointed at stderr for the run and the line is written to the saved descriptor at the end.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

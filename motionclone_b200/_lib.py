@@ -7,8 +7,9 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint8, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# MC_LIB: path of an alternative build of the same library (tile-shape experiments in scripts/; same ABI, same symbols)
-LIB_PATH = os.environ.get("MC_LIB") or os.path.join(_HERE, "libmotionclone_b200.so")
+# The one library this package loads. (A/B scripts under scripts/ point this attribute at a side-by-side build of the same
+# sources BEFORE the first call - scripts/build_variant.sh; nothing in the package or in the environment selects a library.)
+LIB_PATH = os.path.join(_HERE, "libmotionclone_b200.so")
 
 
 class TemporalLayout(Structure):

@@ -1,5 +1,5 @@
 #!/bin/bash
-# build_variant.sh NAME "-DFOO=1 ..." file.cu [file.cu ...]: a side-by-side library for A/B runs (MC_LIB=... python ...):
+# build_variant.sh NAME "-DFOO=1 ..." file.cu [file.cu ...]: a side-by-side library for A/B runs (python scripts/sattn_bench.py --lib motionclone_b200/libmc_variant_NAME.so):
 # the named sources are recompiled with the extra defines, every other object comes from the regular build.
 set -e
 cd "$(dirname "$0")/.."

@@ -6,7 +6,13 @@ import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
-from motionclone_b200 import ops
+from motionclone_b200 import _lib, ops
+
+# `--lib PATH`: time a side-by-side build of the same sources (scripts/build_variant.sh) instead of the in-tree library
+if "--lib" in sys.argv:
+    i = sys.argv.index("--lib")
+    _lib.LIB_PATH = os.path.abspath(sys.argv[i + 1])
+    del sys.argv[i:i + 2]
 
 dev = "cuda"
 

@@ -126,3 +126,40 @@ def test_two_rank_gloo_broadcast(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, out.decode()
+
+
+def test_bench_result_line_is_alone_on_stdout():
+    """bench.py's contract is ONE JSON line on stdout; library banners written to fd 1 during the run (NCCL's version line)
+    must end up on stderr."""
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; sys.stdout.flush(); bench._RESULT_FD = os.dup(1); "
+            "os.dup2(2, 1); os.write(1, b'NCCL version x\\n'); print('python-level noise'); bench._emit({'a': 1})" % root)
+    r = subprocess.run([_sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"a": 1}\n'
+    assert "NCCL version x" in r.stderr and "python-level noise" in r.stderr
+
+
+def test_linear_into_residual_accumulates_in_place_only_without_grad():
+    """spatial.linear_into_residual: the no-grad forwards accumulate the beta = 1 GEMM INTO the residual stream (no memcpy of
+    the activation); under autograd the stream tensor is left untouched (it is saved by the LayerNorm that read it)."""
+    import torch
+    from motionclone_b200.spatial import linear_into_residual
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(24, 16, bias=True)
+    x = torch.randn(2, 5, 24)
+    res = torch.randn(2, 5, 16)
+    want = res + x @ lin.weight.t()  # the projection's bias is carried by the stream, not added here
+    with torch.no_grad():
+        r = res.clone()
+        out = linear_into_residual(x, lin, r)
+        assert out.data_ptr() == r.data_ptr()
+        assert torch.allclose(out, want, atol=1e-5)
+    r = res.clone().requires_grad_(True)
+    out = linear_into_residual(x, lin, r)
+    assert out.data_ptr() != r.data_ptr() and torch.equal(r.detach(), res)
+    assert torch.allclose(out, want, atol=1e-5)
+    out.sum().backward()
+    assert torch.allclose(r.grad, torch.ones_like(res))
