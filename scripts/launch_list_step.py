@@ -9,7 +9,8 @@ from bench import CONFIGS
 INFER = {k: v for k, v in CONFIGS['object'].items() if k not in ('workload', 'distinct_prompts')}
 
 dev = torch.device("cuda:0")
-pipe = mc.build_pipeline(UNET_SD15_CONFIG, dict(INFER), device=dev)
+# eager launches (no CUDA-graph capture: its warm-up forwards would triple the list), like bench.py's roofline leg
+pipe = mc.build_pipeline(UNET_SD15_CONFIG, dict(INFER), device=dev, use_cuda_graphs=False)
 inp = synthetic_inputs(16, 512, 512, 768, 42)
 h = lambda t: t.to(dev, torch.float16)
 pipe.set_prompt_embeds(h(inp["text_embeddings"]))
