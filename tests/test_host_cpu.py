@@ -189,3 +189,26 @@ def test_exp2_polynomial_coefficients_accuracy():
     want = np.exp2(x.astype(np.float64))
     rel = np.abs(got / want - 1.0).max()
     assert rel < 5e-6, rel
+
+
+def test_fold_residual_biases_algebra():
+    """spatial.fold_residual_biases: shifting the residual stream by the sum of a block's output biases and taking the
+    remaining shift back out in front of every sub-block is the SAME function as adding each bias after its projection
+    (attention.py:271-300). Checked in fp64 with arbitrary sub-block functions, including a missing bias."""
+    import torch
+    from motionclone_b200.spatial import fold_residual_biases
+    torch.manual_seed(1)
+    C = 12
+    ws = [torch.randn(C, C, dtype=torch.float64) * 0.3 for _ in range(3)]
+    fs = [lambda u, w=w: torch.tanh(u) @ w for w in ws]          # f_i: any function of the (un-shifted) stream
+    for biases in ([torch.randn(C, dtype=torch.float64) for _ in range(3)],
+                   [torch.randn(C, dtype=torch.float64), None, torch.randn(C, dtype=torch.float64)]):
+        t = torch.randn(5, C, dtype=torch.float64)
+        want = t
+        for f, b in zip(fs, biases):
+            want = want + f(want) + (b if b is not None else 0)
+        shift, pre = fold_residual_biases(biases)
+        s = t + shift                                              # what proj_in's folded bias produces
+        for f, pb in zip(fs, pre):
+            s = s + f(s + pb)                                      # beta = 1 GEMM into the stream; LN sees stream + pre_bias
+        assert torch.allclose(s, want, atol=1e-12)
